@@ -1,0 +1,65 @@
+"""Builds libb200rt.so (CUDA kernels + C ABI) in-tree for sm_100a.
+
+    python -m cpp_raytracer_b200.build [--force] [--verbose]
+
+nvcc cross-compiles without a GPU.  -fmad=false is REQUIRED for parity: the FP64 primitive
+tests must not be contracted into FMAs (the reference is built for baseline x86-64, which has
+none), see csrc/traverse.cuh.  Places that want an FMA call __fmaf_rn explicitly.
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libb200rt.so")
+SOURCES = ["api.cu", "kernels.cu", "bvh_builder.cpp"]
+HEADERS = ["bvh_builder.h", "kernels.h", "thread_pool.h", "traverse.cuh", "shade.cuh", "rng.cuh",
+           os.path.join("..", "..", "include", "b200rt.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-O3", "-lineinfo", "-std=c++17", "-fmad=false",
+    "-ccbin", "g++",
+    "-Xcompiler", "-fPIC,-pthread,-ffp-contract=off,-O3",
+    "-Xptxas", "-v",
+    "-shared",
+]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-lpthread"]
+    env = dict(os.environ)
+    env.pop("CXX", None)   # this image exports a CXX wrapper without libgomp specs
+    env.pop("CC", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    log = res.stdout + res.stderr
+    with open(os.path.join(HERE, "build.log"), "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if verbose or res.returncode != 0:
+        sys.stderr.write(log)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed building libb200rt.so (see cpp_raytracer_b200/build.log)")
+    return LIB
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--force", action="store_true")
+    ap.add_argument("--verbose", action="store_true")
+    a = ap.parse_args()
+    print(build(force=a.force, verbose=a.verbose))

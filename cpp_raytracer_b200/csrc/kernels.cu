@@ -1,0 +1,184 @@
+// kernels.cu -- the CUDA kernels behind the C ABI (sm_100a only; compiled with -fmad=false so
+// FP64 primitive tests reproduce the reference's unfused arithmetic bit for bit).
+//
+//   raycast_kernel        one thread per ray, closest hit -> (canonical prim index, t)
+//                         [BVH::hit_by / Scene::hit_by, reference bvh.h:585-715, scene.h:59-75]
+//   path_megakernel       one thread per pixel, loops over that pixel's samples with path
+//                         regeneration: a lane whose path ended starts its next sample in the same
+//                         loop iteration, so lanes only idle once their pixel is out of samples
+//                         [Camera::render<T> + ray_color, reference camera.h:205-297]
+//   tonemap_kernel        Reinhard + gamma 2 + int(255.999999 v)   [RGB::as_string, rgb.h:90-113]
+#include "kernels.h"
+#include "shade.cuh"
+
+namespace b200rt {
+
+// ------------------------------------------------------------------------------------------
+template <int STACK>
+__global__ void __launch_bounds__(128) raycast_kernel(DeviceScene S, const double *__restrict__ rays, long long n,
+                                                      double tmin, double tmax, int32_t *__restrict__ prim_out,
+                                                      double *__restrict__ t_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double *r = rays + i * 6;
+    const Hit h = closest_hit<STACK, false>(S, r[0], r[1], r[2], r[3], r[4], r[5], tmin, tmax, nullptr);
+    if (h.ref == kNoHit) {
+        prim_out[i] = -1;
+        t_out[i] = 0.0;
+    } else {
+        prim_out[i] = (int32_t)canonical_prim(S, h.ref);
+        t_out[i] = h.t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Thread -> pixel: a block is an 8x8 pixel tile, each warp an 8x4 sub-tile, so the 32 primary
+// rays of a warp are neighbours on the image plane.
+template <int STACK, bool COUNT>
+__global__ void __launch_bounds__(kPathBlock) path_megakernel(const __grid_constant__ RenderParams P) {
+    const CameraParams &C = P.cam;
+    const uint32_t tiles_x = (C.w + 7u) >> 3;
+    const uint32_t tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    const uint32_t px = tile_x * 8u + (threadIdx.x & 7u), py = tile_y * 8u + (threadIdx.x >> 3);
+    const bool valid = px < C.w && py < C.h;
+    const uint32_t pixel = py * C.w + px;
+
+    float sum_r = 0.f, sum_g = 0.f, sum_b = 0.f;
+    unsigned long long rays = 0;
+    TraversalCounters ctr;
+
+    if (valid && C.max_depth > 0) {
+        PathState p;
+        uint32_t s = 0, bounce = 0;
+        bool alive = false;
+        const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
+        while (true) {
+            if (!alive) {
+                if (s == P.sample_count) break;
+                const Philox4 rnd = philox4x32_10(pixel, P.sample_begin + s, 0u, 0u, k0, k1);
+                camera_ray(C, px, py, rnd, p);
+                bounce = 0;
+                alive = true;
+            }
+            // world.hit_by(ray, Interval::with_min(0.00001))  (camera.h:217)
+            const Hit h = closest_hit<STACK, COUNT>(P.scene, p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, 0.00001,
+                                                    __longlong_as_double(0x7ff0000000000000LL), &ctr);
+            ++rays;
+            bool cont;
+            if (h.ref == kNoHit) {
+                p.lr += p.tr * C.background[0]; p.lg += p.tg * C.background[1]; p.lb += p.tb * C.background[2];
+                cont = false;   // camera.h:248
+            } else {
+                const Philox4 rnd = philox4x32_10(pixel, P.sample_begin + s, bounce + 1u, 0u, k0, k1);
+                cont = shade_hit(P.scene, h, rnd, p);
+                // ray_color(scattered, depth_left - 1): contributes nothing once depth_left hits 0 (camera.h:211-213)
+                if (cont && ++bounce == C.max_depth) cont = false;
+            }
+            if (!cont) {
+                sum_r += p.lr; sum_g += p.lg; sum_b += p.lb;
+                alive = false;
+                ++s;
+            }
+        }
+    }
+    if (valid) {
+        float *o = P.out + (size_t)pixel * 3;
+        const float k = P.scale;
+        if (P.flags & kRenderAccumulate) { o[0] += sum_r * k; o[1] += sum_g * k; o[2] += sum_b * k; }
+        else { o[0] = sum_r * k; o[1] = sum_g * k; o[2] = sum_b * k; }
+    }
+    // counters: one atomic per warp
+    for (int off = 16; off; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
+    if ((threadIdx.x & 31) == 0 && rays) atomicAdd(&P.counters[0], rays);
+    if (COUNT) {
+        unsigned long long a = ctr.nodes, b = ctr.prims;
+        for (int off = 16; off; off >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, off);
+            b += __shfl_down_sync(0xffffffffu, b, off);
+        }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&P.counters[1], a); atomicAdd(&P.counters[2], b); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void tonemap_kernel(const float *__restrict__ hdr, long long n_pixels, int32_t *__restrict__ out, int clamp) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    const double r = hdr[i * 3 + 0], g = hdr[i * 3 + 1], b = hdr[i * 3 + 2];
+    const double L = 0.2126 * r + 0.7152 * g + 0.0722 * b;          // rgb.h:28-30
+    const double scale = 255 + 0.999999;                             // rgb.h:106
+    const double v[3] = {r / (1 + L), g / (1 + L), b / (1 + L)};     // rgb.h:99-104
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int q = (int)(scale * sqrt(v[c]));                           // pow(v, 1/2), truncation (rgb.h:107-111)
+        if (clamp) q = q < 0 ? 0 : (q > 255 ? 255 : q);
+        out[i * 3 + c] = q;
+    }
+}
+
+// Frame epilogue on the reducing rank: sum -> mean in place (pixel_color /= spp, camera.h:290) and,
+// optionally, the tone-mapped integers of the same pixels in the same pass.
+__global__ void finalize_kernel(float *__restrict__ frame, long long n_pixels, float scale, int32_t *__restrict__ ldr, int clamp) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pixels) return;
+    const float rf = frame[i * 3 + 0] * scale, gf = frame[i * 3 + 1] * scale, bf = frame[i * 3 + 2] * scale;
+    frame[i * 3 + 0] = rf; frame[i * 3 + 1] = gf; frame[i * 3 + 2] = bf;
+    if (ldr) {
+        const double r = rf, g = gf, b = bf;
+        const double L = 0.2126 * r + 0.7152 * g + 0.0722 * b;
+        const double s255 = 255 + 0.999999;
+        const double v[3] = {r / (1 + L), g / (1 + L), b / (1 + L)};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int q = (int)(s255 * sqrt(v[c]));
+            if (clamp) q = q < 0 ? 0 : (q > 255 ? 255 : q);
+            ldr[i * 3 + c] = q;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+template <int STACK>
+static cudaError_t launch_raycast_t(const DeviceScene &S, const double *rays, long long n, double tmin, double tmax,
+                                    int32_t *prim, double *t, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const int block = 128;
+    raycast_kernel<STACK><<<(unsigned)((n + block - 1) / block), block, 0, st>>>(S, rays, n, tmin, tmax, prim, t);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_raycast(int stack, const DeviceScene &S, const double *rays, long long n, double tmin, double tmax,
+                           int32_t *prim, double *t, cudaStream_t st) {
+    if (stack <= 32) return launch_raycast_t<32>(S, rays, n, tmin, tmax, prim, t, st);
+    if (stack <= 64) return launch_raycast_t<64>(S, rays, n, tmin, tmax, prim, t, st);
+    return launch_raycast_t<128>(S, rays, n, tmin, tmax, prim, t, st);
+}
+
+template <int STACK>
+static cudaError_t launch_path_t(const RenderParams &P, bool count, cudaStream_t st) {
+    const uint32_t tiles = ((P.cam.w + 7u) >> 3) * ((P.cam.h + 7u) >> 3);
+    if (tiles == 0) return cudaSuccess;
+    if (count) path_megakernel<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
+    else path_megakernel<STACK, false><<<tiles, kPathBlock, 0, st>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, cudaStream_t st) {
+    if (stack <= 32) return launch_path_t<32>(P, count, st);
+    if (stack <= 64) return launch_path_t<64>(P, count, st);
+    return launch_path_t<128>(P, count, st);
+}
+
+cudaError_t launch_tonemap(const float *hdr, long long n_pixels, int32_t *out, int clamp, cudaStream_t st) {
+    if (n_pixels == 0) return cudaSuccess;
+    tonemap_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, st>>>(hdr, n_pixels, out, clamp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_finalize(float *frame, long long n_pixels, float scale, int32_t *ldr, int clamp, cudaStream_t st) {
+    if (n_pixels == 0) return cudaSuccess;
+    finalize_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, st>>>(frame, n_pixels, scale, ldr, clamp);
+    return cudaGetLastError();
+}
+
+}  // namespace b200rt

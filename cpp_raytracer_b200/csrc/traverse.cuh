@@ -1,0 +1,217 @@
+// traverse.cuh -- device scene layout + closest-hit traversal shared by every kernel.
+//
+// Stands in for BVH::hit_by (reference include/acceleration/bvh.h:585-715),
+// AABB::is_hit_by_optimized (aabb.h:132-174), Sphere::hit_by (sphere.h:45-96) and
+// Parallelogram::hit_by (parallelogram.h:177-240).
+//
+// Precision design (DESIGN.md "Precision"):
+//  * Box tests run in FP32 on bounds rounded outward, with the ray origin's FP32 rounding error
+//    folded into a per-axis additive pad and a multiplicative slack on the final comparison, so
+//    a box test can only err towards "hit".  They never decide the answer, only prune.
+//  * Primitive tests run in FP64, operation for operation as the reference writes them, and this
+//    translation unit is compiled with -fmad=false (the reference is built for baseline x86-64,
+//    no FMA contraction), so for the same ray the hit time is bit-identical to the reference's.
+//  * Exact ties in t resolve to the lowest canonical primitive index (what Scene::hit_by,
+//    scene.h:59-75, returns), independent of the tree.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200rt {
+
+struct DeviceMaterial {   // 32 B, two 16-byte loads
+    float r, g, b;        // colour; for lights: intensity * colour (material.h:261-263)
+    uint32_t kind;
+    double param;         // fuzz | refractive index | intensity
+    double pad;
+};
+
+struct DeviceScene {
+    const float4 *nodes;        // 8 x float4 per 4-wide node (bvh_builder.h Node4)
+    const double2 *spheres;     // 2 x double2 per sphere, leaf order: {cx, cy}, {cz, r}
+    const uint2 *sphere_meta;   // {canonical prim index, material index}
+    const double2 *quads;       // 8 x double2 per quad, leaf order: n^[3] V[3] w[3] s1[3] s2[3] pad
+    const uint2 *quad_meta;
+    const DeviceMaterial *materials;
+};
+
+constexpr uint32_t kLeafFlagD = 0x80000000u;
+constexpr uint32_t kQuadFlagD = 0x40000000u;
+constexpr uint32_t kNoHit = 0xFFFFFFFFu;
+constexpr float kBoxSlack = 1.0f + 1e-6f;      // covers 3 roundings (2^-24 each) on both sides
+
+struct Hit {
+    double t;
+    uint32_t ref;   // kNoHit, or (kQuadFlagD?) | index into the leaf-ordered per-type array
+};
+
+struct TraversalCounters {
+    unsigned long long nodes = 0, prims = 0;
+};
+
+__device__ __forceinline__ uint32_t canonical_prim(const DeviceScene &S, uint32_t ref) {
+    return (ref & kQuadFlagD) ? __ldg(&S.quad_meta[ref & ~kQuadFlagD]).x : __ldg(&S.sphere_meta[ref]).x;
+}
+
+// Sphere::hit_by (sphere.h:45-96).  `a` = dot(dir, dir) is hoisted out (same operations, same
+// order, so the same bits).  Returns the accepted root or a NaN-free "no" via `ok`.
+__device__ __forceinline__ bool sphere_root(double ox, double oy, double oz, double dx, double dy, double dz,
+                                            double a, double cx, double cy, double cz, double r,
+                                            double tmin, double tmax, bool tie_ok, double &root_out) {
+    const double ocx = ox - cx, ocy = oy - cy, ocz = oz - cz;
+    const double b_half = dx * ocx + dy * ocy + dz * ocz;
+    const double c = (ocx * ocx + ocy * ocy + ocz * ocz) - r * r;
+    const double disc = b_half * b_half - a * c;
+    if (disc < 0) return false;
+    const double sq = sqrt(disc);
+    double root = (-b_half - sq) / a;
+    // Interval::contains_exclusive (interval.h:38); `tie_ok` additionally admits root == tmax so
+    // that the caller can break the tie by primitive index.
+    if (!(tmin < root && (root < tmax || (tie_ok && root == tmax)))) {
+        root = (-b_half + sq) / a;
+        if (!(tmin < root && (root < tmax || (tie_ok && root == tmax)))) return false;
+    }
+    root_out = root;
+    return true;
+}
+
+// Parallelogram::hit_by (parallelogram.h:177-240) with the constructor's precomputed
+// unit_plane_normal / scaled_plane_normal (parallelogram.h:269-279) supplied by the host.
+__device__ __forceinline__ bool quad_root(double ox, double oy, double oz, double dx, double dy, double dz,
+                                          const double2 *__restrict__ q, double tmin, double tmax,
+                                          bool tie_ok, double &t_out) {
+    const double2 q0 = __ldg(q + 0), q1 = __ldg(q + 1), q2 = __ldg(q + 2);
+    const double nx = q0.x, ny = q0.y, nz = q1.x, vx = q1.y, vy = q2.x, vz = q2.y;
+    const double den = nx * dx + ny * dy + nz * dz;
+    if (fabs(den) < 1e-9) return false;
+    const double ex = vx - ox, ey = vy - oy, ez = vz - oz;
+    const double t = (nx * ex + ny * ey + nz * ez) / den;
+    if (!(tmin < t && (t < tmax || (tie_ok && t == tmax)))) return false;
+    const double2 q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5), q6 = __ldg(q + 6), q7 = __ldg(q + 7);
+    const double wx = q3.x, wy = q3.y, wz = q4.x;
+    const double s1x = q4.y, s1y = q5.x, s1z = q5.y;
+    const double s2x = q6.x, s2y = q6.y, s2z = q7.x;
+    const double px = (ox + t * dx) - vx, py = (oy + t * dy) - vy, pz = (oz + t * dz) - vz;
+    // alpha = dot(w, cross(p, s2)); beta = dot(w, cross(s1, p))
+    const double c1x = py * s2z - pz * s2y, c1y = pz * s2x - px * s2z, c1z = px * s2y - py * s2x;
+    const double alpha = wx * c1x + wy * c1y + wz * c1z;
+    const double c2x = s1y * pz - s1z * py, c2y = s1z * px - s1x * pz, c2z = s1x * py - s1y * px;
+    const double beta = wx * c2x + wy * c2y + wz * c2z;
+    if (!(0 <= alpha && alpha <= 1 && 0 <= beta && beta <= 1)) return false;
+    t_out = t;
+    return true;
+}
+
+#define B200RT_CSWAP(a, b) { const uint32_t lo_ = min(a, b); b = max(a, b); a = lo_; }
+
+template <int STACK, bool COUNT>
+__device__ __forceinline__ Hit closest_hit(const DeviceScene &S, double ox, double oy, double oz,
+                                           double dx, double dy, double dz, double tmin, double tmax,
+                                           TraversalCounters *ctr) {
+    // ---- per-ray setup for the FP32 box tests -------------------------------------------
+    const float fox = (float)ox, foy = (float)oy, foz = (float)oz;
+    // 1/d in FP32.  A zero component gives +-inf on purpose: (plane - o) * inf is -inf / +inf when
+    // the origin is strictly inside / outside the slab and NaN when it lies exactly on the plane;
+    // fmaxf/fminf drop NaN operands, i.e. "no constraint from this axis", which is the right
+    // answer for a ray travelling inside a slab's boundary plane.  (The reference's own slab
+    // test, aabb.h:132-174, mishandles -0.0 here; ours does not depend on the sign of zero.)
+    const float fix = (float)(1.0 / dx), fiy = (float)(1.0 / dy), fiz = (float)(1.0 / dz);
+    // additive pad in t-space for the origin's rounding to FP32 (exact per ray, rounded up);
+    // exactly representable origins need none (and must not produce 0 * inf).
+    const double rx = fabs(ox - (double)fox), ry = fabs(oy - (double)foy), rz = fabs(oz - (double)foz);
+    const float eox = rx == 0.0 ? 0.0f : __double2float_ru(rx * (double)fabsf(fix) * 1.00001);
+    const float eoy = ry == 0.0 ? 0.0f : __double2float_ru(ry * (double)fabsf(fiy) * 1.00001);
+    const float eoz = rz == 0.0 ? 0.0f : __double2float_ru(rz * (double)fabsf(fiz) * 1.00001);
+    // which float4 of the node holds the near plane on each axis (lo if dir >= 0, hi otherwise)
+    const int nearx = fix < 0.0f ? 1 : 0, neary = fiy < 0.0f ? 3 : 2, nearz = fiz < 0.0f ? 5 : 4;
+    const int farx = nearx ^ 1, fary = neary ^ 1, farz = nearz ^ 1;
+    const float tmin32 = __double2float_rd(tmin);
+    float tmax32 = __double2float_ru(tmax);
+
+    const double a = dx * dx + dy * dy + dz * dz;   // sphere.h:49
+
+    uint2 stack[STACK];
+    int sp = 0;
+    uint32_t cur = 0;   // root
+    Hit best{tmax, kNoHit};
+
+    while (true) {
+        if (!(cur & kLeafFlagD)) {
+            // ---------------- interior: test the four child boxes ------------------------
+            const float4 *n = S.nodes + (size_t)cur * 8;
+            const float4 bnx = __ldg(n + nearx), bfx = __ldg(n + farx);
+            const float4 bny = __ldg(n + neary), bfy = __ldg(n + fary);
+            const float4 bnz = __ldg(n + nearz), bfz = __ldg(n + farz);
+            const int4 ch = __ldg((const int4 *)(n + 6));
+            if (COUNT) ctr->nodes++;
+            const float tfar_cap = tmax32;
+#define B200RT_SLOT(c, k)                                                                                  \
+            uint32_t key##k;                                                                               \
+            {                                                                                              \
+                const float tn = fmaxf(fmaxf(__fmaf_rn(bnx.c - fox, fix, -eox), __fmaf_rn(bny.c - foy, fiy, -eoy)), \
+                                       fmaxf(__fmaf_rn(bnz.c - foz, fiz, -eoz), tmin32));                   \
+                const float tf = fminf(fminf(__fmaf_rn(bfx.c - fox, fix, eox), __fmaf_rn(bfy.c - foy, fiy, eoy)),   \
+                                       fminf(__fmaf_rn(bfz.c - foz, fiz, eoz), tfar_cap));                  \
+                key##k = (tn <= tf * kBoxSlack) ? ((__float_as_uint(tn) & ~3u) | k) : 0xFFFFFFFFu;          \
+            }
+            B200RT_SLOT(x, 0) B200RT_SLOT(y, 1) B200RT_SLOT(z, 2) B200RT_SLOT(w, 3)
+#undef B200RT_SLOT
+            // sort the four keys ascending (nearest first); misses sink to the end
+            B200RT_CSWAP(key0, key1) B200RT_CSWAP(key2, key3) B200RT_CSWAP(key0, key2)
+            B200RT_CSWAP(key1, key3) B200RT_CSWAP(key1, key2)
+#define B200RT_CHILD(key) ((uint32_t)(((key) & 3u) == 0 ? ch.x : ((key) & 3u) == 1 ? ch.y : ((key) & 3u) == 2 ? ch.z : ch.w))
+            if (key0 != 0xFFFFFFFFu) {
+                if (key3 != 0xFFFFFFFFu) stack[sp++] = make_uint2(B200RT_CHILD(key3), key3);
+                if (key2 != 0xFFFFFFFFu) stack[sp++] = make_uint2(B200RT_CHILD(key2), key2);
+                if (key1 != 0xFFFFFFFFu) stack[sp++] = make_uint2(B200RT_CHILD(key1), key1);
+                cur = B200RT_CHILD(key0);
+                continue;
+            }
+#undef B200RT_CHILD
+        } else {
+            // ---------------- leaf: FP64 primitive tests ----------------------------------
+            const uint32_t cnt = (cur >> 26) & 0xFu, first = cur & 0x03FFFFFFu;
+            if (cur & kQuadFlagD) {
+                for (uint32_t i = 0; i < cnt; ++i) {
+                    if (COUNT) ctr->prims++;
+                    double t;
+                    if (quad_root(ox, oy, oz, dx, dy, dz, S.quads + (size_t)(first + i) * 8, tmin, best.t,
+                                  best.ref != kNoHit, t)) {
+                        const uint32_t ref = kQuadFlagD | (first + i);
+                        if (t < best.t || canonical_prim(S, ref) < canonical_prim(S, best.ref)) {
+                            best.t = t;
+                            best.ref = ref;
+                            tmax32 = __double2float_ru(t);
+                        }
+                    }
+                }
+            } else {
+                for (uint32_t i = 0; i < cnt; ++i) {
+                    if (COUNT) ctr->prims++;
+                    const double2 s0 = __ldg(S.spheres + (size_t)(first + i) * 2);
+                    const double2 s1 = __ldg(S.spheres + (size_t)(first + i) * 2 + 1);
+                    double t;
+                    if (sphere_root(ox, oy, oz, dx, dy, dz, a, s0.x, s0.y, s1.x, s1.y, tmin, best.t,
+                                    best.ref != kNoHit, t)) {
+                        const uint32_t ref = first + i;
+                        if (t < best.t || canonical_prim(S, ref) < canonical_prim(S, best.ref)) {
+                            best.t = t;
+                            best.ref = ref;
+                            tmax32 = __double2float_ru(t);
+                        }
+                    }
+                }
+            }
+        }
+        // ---------------- pop, skipping entries that can no longer contain a closer hit -------
+        bool got = false;
+        while (sp > 0) {
+            const uint2 e = stack[--sp];
+            if (__uint_as_float(e.y & ~3u) <= tmax32 * kBoxSlack) { cur = e.x; got = true; break; }
+        }
+        if (!got) break;
+    }
+    return best;
+}
+
+}  // namespace b200rt

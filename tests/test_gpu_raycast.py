@@ -1,0 +1,89 @@
+"""GPU parity, check 1 of the north star: the deterministic ray-cast harness.
+
+Fixed ray sets (camera rays with a fixed jitter table, rays recorded from the reference's own
+paths, adversarial rays) are cast through the C ABI (b200rt_raycast -> raycast_kernel) and
+compared with what the reference itself returned for them (tests/golden/*.hits*.gz, generated
+by tests/golden/make_golden.py from oracle/_ref/ref_bridge):
+
+  * against Scene::hit_by (reference scene.h:59-75): primitive index BIT-EXACT and t BIT-EXACT
+    on every ray (stronger than the 1e-5 relative the north star asks for), ties included;
+  * against BVH::hit_by (reference bvh.h:585-715): identical except on rays where the reference
+    disagrees with ITSELF (BVH vs Scene), which are counted and must all be degenerate
+    (a zero direction component: 1/-0 = -inf breaks aabb.h:132-174) or exact ties in t.
+"""
+import numpy as np
+import pytest
+
+from conftest import SMALL_SCENES
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-5   # the north star's bound on t; we additionally require bit equality below
+
+
+@pytest.mark.parametrize("name", SMALL_SCENES)
+def test_raycast_matches_reference(golden, name):
+    import cpp_raytracer_b200 as rt
+    scene = golden.scene(name)
+    rays, tmin, tmax = golden.rays(name)
+    with rt.DeviceSceneHandle(scene) as dev:
+        prim, t = dev.raycast(rays, tmin, tmax)
+    # --- vs Scene::hit_by (brute force): exact ---
+    pb, tb = golden.hits(name, brute=True)
+    bad = np.nonzero((prim != pb) | (t != tb))[0]
+    assert len(bad) == 0, (f"{name}: {len(bad)} rays differ from Scene::hit_by; first: ray {bad[0]} {rays[bad[0]]} "
+                           f"got ({prim[bad[0]]}, {t[bad[0]]!r}) want ({pb[bad[0]]}, {tb[bad[0]]!r})")
+    hit = pb >= 0
+    assert np.all(np.abs(t[hit] - tb[hit]) <= REL_TOL * np.abs(tb[hit]))
+    # --- vs BVH::hit_by: equal except where the reference disagrees with itself ---
+    pv, tv = golden.hits(name, brute=False)
+    diff = np.nonzero((prim != pv) | (t != tv))[0]
+    ref_self_disagrees = (pv != pb) | (tv != tb)
+    assert np.all(ref_self_disagrees[diff]), f"{name}: differs from BVH::hit_by where the reference agrees with itself"
+    degenerate = (rays[diff, 3:] == 0).any(axis=1)
+    tie = (tv[diff] == t[diff]) & (pv[diff] >= 0) & (prim[diff] >= 0)
+    assert np.all(degenerate | tie), f"{name}: non-degenerate, non-tie disagreement with BVH::hit_by"
+    print(f"{name}: {len(rays)} rays exact vs Scene::hit_by; vs BVH::hit_by {len(diff)} logged "
+          f"({int(tie.sum())} exact ties, {int((degenerate & ~tie).sum())} zero-direction-component rays)")
+
+
+def test_raycast_interval_and_empty(golden):
+    """tmin/tmax are exclusive (interval.h:38); empty inputs and empty scenes are fine."""
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    scene = golden.scene("quads")
+    with rt.DeviceSceneHandle(scene) as dev:
+        prim, t = dev.raycast(np.zeros((0, 6)))
+        assert prim.shape == (0,) and t.shape == (0,)
+        ray = np.array([[0.0, 0.0, 9.0, 0.0, 0.0, -1.0]])   # hits the back quad z=0 at t=9
+        p, tt = dev.raycast(ray, 1e-5, np.inf)
+        assert p[0] == 1 and tt[0] == 9.0
+        p, _ = dev.raycast(ray, 1e-5, 9.0)      # exclusive upper bound
+        assert p[0] == -1
+        p, _ = dev.raycast(ray, 9.0, np.inf)    # exclusive lower bound
+        assert p[0] == -1
+        p, tt = dev.raycast(ray, 8.999999, 9.000001)
+        assert p[0] == 1 and tt[0] == 9.0
+    empty = capi.HostScene(np.zeros(0, capi.MATERIAL_DTYPE), np.zeros(0, capi.SPHERE_DTYPE),
+                           np.zeros(0, capi.QUAD_DTYPE), scene.camera)
+    with rt.DeviceSceneHandle(empty) as dev:
+        p, _ = dev.raycast(np.array([[0.0, 0, 0, 0, 0, -1]]))
+        assert p[0] == -1
+        img, st = dev.render(rt.camera_with(scene.camera, image_w=16, image_h=8, spp=2))
+        assert np.allclose(img, np.asarray(scene.camera["background"][0], dtype=np.float32))
+        assert st["rays"] == 16 * 8 * 2
+
+
+def test_raycast_error_paths(golden):
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    scene = golden.scene("quads")
+    bad = capi.HostScene(scene.materials.copy(), scene.spheres, scene.quads.copy(), scene.camera)
+    bad.quads["mat"][0] = 99
+    with pytest.raises(rt.B200rtError) as e:
+        rt.DeviceSceneHandle(bad)
+    assert e.value.code == capi.EINVAL
+    bad2 = capi.HostScene(scene.materials.copy(), scene.spheres, scene.quads, scene.camera)
+    bad2.materials["kind"][0] = 7      # unknown Material subclass -> error, never a guess
+    with pytest.raises(rt.B200rtError):
+        rt.DeviceSceneHandle(bad2)
