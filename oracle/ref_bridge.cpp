@@ -28,6 +28,7 @@
 //     render <out.hdr> [seed]                  Camera::render<BVH> unmodified (camera.h:264-297)
 //     stats                                    rays/path, node visits/ray, prim tests/ray
 //     kat <out.json>                           unit known-answers (reflect/refract/tonemap/LCG)
+//     lcg_state                                main thread's LCG state (consumes one draw)
 // Every command prints one JSON line on stdout; the reference's own chatter is swallowed.
 
 #include "util/rand_util.h"
@@ -462,6 +463,12 @@ int main(int argc, char **argv) {
             o.write((const char *)hdr, 16);
             o.write((const char *)px.data(), px.size() * 8);
             std::printf("{\"cmd\":\"render_f64\",\"w\":%zu,\"h\":%zu}\n", w, h);
+        } else if (cmd == "lcg_state") {
+            // The calling thread's LCG state (rand_util.h:106) is a function-local thread_local and
+            // cannot be read; draw once and invert rand_double(): state = v * (2^32 - 2), exact.
+            const double v = rand_double();
+            const uint32_t st = (uint32_t)std::llround(v * 4294967294.0);
+            std::printf("{\"cmd\":\"lcg_state\",\"state_after_this_draw\":%u}\n", st);
         } else if (cmd == "ppm") {
             // the reference's own writer (image.h:38-56) on the reference's own render
             std::string out = next();
@@ -483,8 +490,11 @@ int main(int argc, char **argv) {
             std::ofstream o(out);
             o.precision(17);
             o << "{\n";
-            // LCG stream (rand_util.h:85-117): the next 16 rand_double() values of THIS thread
-            o << "\"rand_double_next16\": [";
+            // LCG stream (rand_util.h:51-117).  Only meaningful for scenes that have not drawn a random
+            // number yet (quads, cornell*): seed the sequence with 12345, then the first draw of this
+            // thread takes its seed from SeedSeqGenerator::next_seed().
+            SeedSeqGenerator::get_instance().set_seed(12345);
+            o << "\"rand_double_seed\": 12345,\n\"rand_double_next16\": [";
             for (int k = 0; k < 16; ++k) o << (k ? "," : "") << rand_double();
             o << "],\n";
             // reflected / refracted / reflectance on fixed inputs

@@ -14,6 +14,8 @@ For every small scene it writes under tests/golden/:
     <scene>.refA.npy.gz / <scene>.refB.npy.gz
                             two statistically independent reference renders (float32 linear HDR)
                             at reduced resolution -> image-convergence tests and their noise floor
+    <scene>.render1t.npz    single-threaded reference render in exact doubles + the LCG state it started
+                            from -> BIT-EXACT pin of the C restatement's whole path loop
     kat.json                unit known answers (LCG stream, reflect/refract/Schlick, tone map)
 The big scenes (raining: 2.2 M quads, millions_lights: 3.1 M spheres) are NOT committed; the
 GPU tests regenerate them on the box with the same bridge binary, which travels with the repo.
@@ -136,10 +138,35 @@ def adversarial_rays(scene, rng):
     return np.array(rays, dtype=np.float64)
 
 
+# single-threaded double-precision renders for the BIT-EXACT pin of the C restatement
+RENDER_1T = {"rtow_final": (24, 16, 4, 20), "rtow_lights": (24, 16, 4, 20), "quads": (16, 16, 4, 50),
+             "cornell": (16, 16, 4, 50), "xmas": (24, 16, 2, 50)}
+
+
+def make_render1t(tmp):
+    for name, (w, h, spp, depth) in RENDER_1T.items():
+        out = os.path.join(tmp, f"{name}.f64")
+        lines = run([name, "--w", str(w), "--h", str(h), "--spp", str(spp), "--depth", str(depth), "--threads", "1",
+                     "lcg_state", "render_f64", out])
+        state = lines[0]["state_after_this_draw"]
+        img = scene_io.load_hdr(out)
+        assert img.dtype == np.float64
+        np.savez_compressed(os.path.join(HERE, f"{name}.render1t.npz"), image=img, lcg_state=np.uint32(state),
+                            w=w, h=h, spp=spp, max_depth=depth)
+        print("render1t", name, state, flush=True)
+
+
 def main():
     if not os.path.exists(BRIDGE):
         sys.exit("build oracle/_ref/ref_bridge first (make -C oracle ref)")
     tmp = tempfile.mkdtemp(prefix="golden_")
+    part = sys.argv[1] if len(sys.argv) > 1 else "all"
+    if part in ("all", "render1t"):
+        make_render1t(tmp)
+    if part in ("all", "kat"):
+        run(["cornell_empty", "kat", os.path.join(HERE, "kat.json")])
+    if part != "all":
+        return
     summary = {}
     for name, (w, h, spp, depth) in SCENES.items():
         rng = np.random.default_rng(abs(hash(name)) % (2**32) if False else sum(map(ord, name)))
@@ -185,7 +212,6 @@ def main():
                     np.save(g, img)
                 summary[name][tag] = {k: info[k] for k in ("w", "h", "spp", "max_depth", "seconds")}
         print(name, json.dumps(summary[name])[:300], flush=True)
-    run(["quads", "kat", os.path.join(HERE, "kat.json")])
     with open(os.path.join(HERE, "golden_summary.json"), "w") as f:
         json.dump(summary, f, indent=1, sort_keys=True)
 

@@ -1,0 +1,51 @@
+"""world_size-2 `gloo` test of the multi-GPU path's host logic (no GPU): the sample split tiles
+[0, spp), and sum-reducing the per-rank frame sums onto rank 0 gives the single-rank sum.  The
+per-rank 'render' is stood in by a deterministic function of (pixel, sample) -- the real kernel
+has the same property (streams keyed by the global sample index), which the GPU test
+test_render_is_deterministic_and_split_invariant checks on the device."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _fake_sample(pix, s):
+    x = (pix * 2654435761 + s * 40503 + 12345) % 1000003
+    return (x.astype(np.float64) / 1000003.0).astype(np.float32)
+
+
+def _frame_sum(h, w, first, count):
+    pix = np.arange(h * w, dtype=np.int64)
+    acc = np.zeros(h * w, np.float32)
+    for s in range(first, first + count):
+        acc += _fake_sample(pix, s)
+    return np.repeat(acc.reshape(h, w, 1), 3, axis=2)
+
+
+def _worker(rank, world, port, spp, h, w, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from cpp_raytracer_b200.dist import reduce_frames, sample_range
+    first, count = sample_range(spp, rank, world)
+    local = torch.from_numpy(_frame_sum(h, w, first, count))
+    reduce_frames(local, dst=0)
+    if rank == 0:
+        np.save(out_path, (local / spp).numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sample_split_reduce_world2_gloo(tmp_path):
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    spp, h, w = 37, 6, 8      # odd spp: ranks get 18 and 19 samples
+    out = str(tmp_path / "frame.npy")
+    mp.spawn(_worker, args=(2, port, spp, h, w, out), nprocs=2, join=True)
+    got = np.load(out)
+    want = _frame_sum(h, w, 0, spp) / spp
+    assert np.allclose(got, want, rtol=1e-5, atol=1e-6)

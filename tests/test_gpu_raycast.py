@@ -87,3 +87,59 @@ def test_raycast_error_paths(golden):
     bad2.materials["kind"][0] = 7      # unknown Material subclass -> error, never a guess
     with pytest.raises(rt.B200rtError):
         rt.DeviceSceneHandle(bad2)
+
+
+def _random_scene(rng, n_sph, n_quad):
+    from cpp_raytracer_b200 import capi
+    sph = np.zeros(n_sph, capi.SPHERE_DTYPE)
+    sph["c"] = rng.uniform(-20, 20, (n_sph, 3))
+    sph["r"] = rng.uniform(0.05, 2.0, n_sph)
+    quads = np.zeros(n_quad, capi.QUAD_DTYPE)
+    quads["v"] = rng.uniform(-20, 20, (n_quad, 3))
+    quads["s1"] = rng.normal(size=(n_quad, 3)) * 3
+    quads["s2"] = rng.normal(size=(n_quad, 3)) * 3
+    order = rng.permutation(n_sph + n_quad)            # canonical order interleaves the two types
+    sph["prim"] = order[:n_sph]
+    quads["prim"] = order[n_sph:]
+    mats = np.zeros(1, capi.MATERIAL_DTYPE)
+    return capi.HostScene(mats, sph, quads, np.zeros(1, capi.CAMERA_DTYPE))
+
+
+@pytest.mark.parametrize("seed,n_sph,n_quad,leaf", [(1, 300, 0, 1), (2, 0, 200, 2), (3, 500, 300, 4), (4, 1, 0, 1), (5, 2000, 500, 8)])
+def test_raycast_vs_c_oracle_on_seeded_random_scenes(seed, n_sph, n_quad, leaf):
+    """CUDA path vs oracle/pt_oracle.c (brute force, Scene::hit_by semantics) on fresh seeded
+    inputs: mixed sphere/quad scenes, rays from inside and outside, every leaf size."""
+    import os, sys
+    import cpp_raytracer_b200 as rt
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pt_oracle
+    rng = np.random.default_rng(seed)
+    scene = _random_scene(rng, n_sph, n_quad)
+    n = 4096
+    o = rng.uniform(-25, 25, (n, 3))
+    d = rng.normal(size=(n, 3)) * rng.uniform(0.1, 10, (n, 1))
+    rays = np.concatenate([o, d], axis=1)
+    want_p, want_t = pt_oracle.raycast_brute(scene, rays, 1e-5, np.inf)
+    with rt.DeviceSceneHandle(scene, max_leaf_prims=leaf) as dev:
+        p, t = dev.raycast(rays, 1e-5, np.inf)
+    assert (want_p >= 0).mean() > 0.05
+    assert np.array_equal(p, want_p) and np.array_equal(t, want_t)
+
+
+def test_raycast_exact_ties_resolve_to_lowest_canonical_index():
+    """Coincident primitives: the lowest canonical index wins (Scene::hit_by, scene.h:59-75),
+    whatever order the tree visits them in."""
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    k = 9
+    sph = np.zeros(k, capi.SPHERE_DTYPE)
+    sph["c"] = [0, 0, -5]
+    sph["r"] = 1.0
+    sph["prim"] = np.arange(k)[::-1]       # stored in reverse canonical order
+    scene = capi.HostScene(np.zeros(1, capi.MATERIAL_DTYPE), sph, np.zeros(0, capi.QUAD_DTYPE), np.zeros(1, capi.CAMERA_DTYPE))
+    rays = np.array([[0.0, 0, 0, 0, 0, -1], [0.3, 0.1, 0, 0, 0, -2]])
+    for leaf in (1, 2, 8):
+        with rt.DeviceSceneHandle(scene, max_leaf_prims=leaf) as dev:
+            p, t = dev.raycast(rays)
+        assert p.tolist() == [0, 0] and t[0] == 4.0
