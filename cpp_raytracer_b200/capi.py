@@ -29,7 +29,7 @@ CAMERA_DTYPE = np.dtype([
 assert MATERIAL_DTYPE.itemsize == 40 and SPHERE_DTYPE.itemsize == 40 and QUAD_DTYPE.itemsize == 80
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_LIGHT = 0, 1, 2, 3
-VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1
+VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT, VARIANT_MEGAKERNEL_VOTED = 0, 1, 2
 FLAG_SUM, FLAG_ACCUMULATE, FLAG_COUNTERS = 1, 2, 4
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, EINTERNAL = 0, -1, -2, -3, -4, -5
 

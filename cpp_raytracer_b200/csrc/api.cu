@@ -221,7 +221,8 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
     if (opts) o = *opts;
     const uint64_t count = o.sample_count ? o.sample_count : cam->spp;
     if (count > 0xFFFFFFFFull || o.sample_offset + count > 0xFFFFFFFFull) return fail(B200RT_EINVAL, "sample range out of range");
-    if (o.variant != B200RT_VARIANT_MEGAKERNEL) return fail(B200RT_EINVAL, "unknown kernel variant");
+    if (o.variant != B200RT_VARIANT_MEGAKERNEL && o.variant != B200RT_VARIANT_MEGAKERNEL_VOTED)
+        return fail(B200RT_EINVAL, "unknown kernel variant");
     P.scene = s->d;
     P.seed = o.seed;
     P.sample_begin = (uint32_t)o.sample_offset;
@@ -232,7 +233,8 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
     P.counters = s->d_counters;
     CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 3 * sizeof(unsigned long long), st));
     CUDA_TRY(cudaEventRecord(s->ev0, st));
-    CUDA_TRY(launch_path_megakernel(s->stack, P, (o.flags & B200RT_FLAG_COUNTERS) != 0, st));
+    CUDA_TRY(launch_path_megakernel(s->stack, P, (o.flags & B200RT_FLAG_COUNTERS) != 0,
+                                    o.variant == B200RT_VARIANT_MEGAKERNEL_VOTED, st));
     CUDA_TRY(cudaEventRecord(s->ev1, st));
     if (stats) {
         std::memset(stats, 0, sizeof *stats);

@@ -3,10 +3,10 @@
 //
 //   raycast_kernel        one thread per ray, closest hit -> (canonical prim index, t)
 //                         [BVH::hit_by / Scene::hit_by, reference bvh.h:585-715, scene.h:59-75]
-//   path_megakernel       one thread per pixel, loops over that pixel's samples with path
-//                         regeneration: a lane whose path ended starts its next sample in the same
-//                         loop iteration, so lanes only idle once their pixel is out of samples
+//   path_megakernel       one thread per pixel, all of that pixel's samples, with path regeneration:
+//                         a lane whose path ended starts its next sample right away
 //                         [Camera::render<T> + ray_color, reference camera.h:205-297]
+//   path_megakernel_voted experiment kept for A/B (variant 2): warp-voted step scheduling
 //   tonemap_kernel        Reinhard + gamma 2 + int(255.999999 v)   [RGB::as_string, rgb.h:90-113]
 #include "kernels.h"
 #include "shade.cuh"
@@ -34,55 +34,27 @@ __global__ void __launch_bounds__(128) raycast_kernel(DeviceScene S, const doubl
 // ------------------------------------------------------------------------------------------
 // Thread -> pixel: a block is an 8x8 pixel tile, each warp an 8x4 sub-tile, so the 32 primary
 // rays of a warp are neighbours on the image plane.
-template <int STACK, bool COUNT>
-__global__ void __launch_bounds__(kPathBlock) path_megakernel(const __grid_constant__ RenderParams P) {
-    const CameraParams &C = P.cam;
+struct PixelMap {
+    uint32_t px, py, pixel;
+    bool valid;
+};
+__device__ __forceinline__ PixelMap map_pixel(const CameraParams &C) {
     const uint32_t tiles_x = (C.w + 7u) >> 3;
     const uint32_t tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
-    const uint32_t px = tile_x * 8u + (threadIdx.x & 7u), py = tile_y * 8u + (threadIdx.x >> 3);
-    const bool valid = px < C.w && py < C.h;
-    const uint32_t pixel = py * C.w + px;
+    PixelMap m;
+    m.px = tile_x * 8u + (threadIdx.x & 7u);
+    m.py = tile_y * 8u + (threadIdx.x >> 3);
+    m.valid = m.px < C.w && m.py < C.h;
+    m.pixel = m.py * C.w + m.px;
+    return m;
+}
 
-    float sum_r = 0.f, sum_g = 0.f, sum_b = 0.f;
-    unsigned long long rays = 0;
-    TraversalCounters ctr;
-
-    if (valid && C.max_depth > 0) {
-        PathState p;
-        uint32_t s = 0, bounce = 0;
-        bool alive = false;
-        const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
-        while (true) {
-            if (!alive) {
-                if (s == P.sample_count) break;
-                const Philox4 rnd = philox4x32_10(pixel, P.sample_begin + s, 0u, 0u, k0, k1);
-                camera_ray(C, px, py, rnd, p);
-                bounce = 0;
-                alive = true;
-            }
-            // world.hit_by(ray, Interval::with_min(0.00001))  (camera.h:217)
-            const Hit h = closest_hit<STACK, COUNT>(P.scene, p.ox, p.oy, p.oz, p.dx, p.dy, p.dz, 0.00001,
-                                                    __longlong_as_double(0x7ff0000000000000LL), &ctr);
-            ++rays;
-            bool cont;
-            if (h.ref == kNoHit) {
-                p.lr += p.tr * C.background[0]; p.lg += p.tg * C.background[1]; p.lb += p.tb * C.background[2];
-                cont = false;   // camera.h:248
-            } else {
-                const Philox4 rnd = philox4x32_10(pixel, P.sample_begin + s, bounce + 1u, 0u, k0, k1);
-                cont = shade_hit(P.scene, h, rnd, p);
-                // ray_color(scattered, depth_left - 1): contributes nothing once depth_left hits 0 (camera.h:211-213)
-                if (cont && ++bounce == C.max_depth) cont = false;
-            }
-            if (!cont) {
-                sum_r += p.lr; sum_g += p.lg; sum_b += p.lb;
-                alive = false;
-                ++s;
-            }
-        }
-    }
-    if (valid) {
-        float *o = P.out + (size_t)pixel * 3;
+__device__ __forceinline__ void write_pixel_and_counters(const RenderParams &P, const PixelMap &m, float sum_r, float sum_g,
+                                                         float sum_b, uint32_t lane_rays, bool count,
+                                                         const TraversalCounters &ctr) {
+    unsigned long long rays = lane_rays;
+    if (m.valid) {
+        float *o = P.out + (size_t)m.pixel * 3;
         const float k = P.scale;
         if (P.flags & kRenderAccumulate) { o[0] += sum_r * k; o[1] += sum_g * k; o[2] += sum_b * k; }
         else { o[0] = sum_r * k; o[1] = sum_g * k; o[2] = sum_b * k; }
@@ -90,7 +62,7 @@ __global__ void __launch_bounds__(kPathBlock) path_megakernel(const __grid_const
     // counters: one atomic per warp
     for (int off = 16; off; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
     if ((threadIdx.x & 31) == 0 && rays) atomicAdd(&P.counters[0], rays);
-    if (COUNT) {
+    if (count) {
         unsigned long long a = ctr.nodes, b = ctr.prims;
         for (int off = 16; off; off >>= 1) {
             a += __shfl_down_sync(0xffffffffu, a, off);
@@ -98,6 +70,116 @@ __global__ void __launch_bounds__(kPathBlock) path_megakernel(const __grid_const
         }
         if ((threadIdx.x & 31) == 0) { atomicAdd(&P.counters[1], a); atomicAdd(&P.counters[2], b); }
     }
+}
+
+// One path segment's worth of "shade + continue or regenerate": consumes the finished traversal
+// in T (if any), and leaves either a new ray in `ray` (returns true) or the lane finished.
+struct LaneState {
+    PathState p;
+    Ray ray;
+    uint32_t s = 0, bounce = 0;
+    bool has_path = false;
+    float sum_r = 0.f, sum_g = 0.f, sum_b = 0.f;   // every contribution (throughput x emission / background) is added here directly
+    uint32_t rays = 0;
+};
+__device__ __forceinline__ bool shade_and_advance(const RenderParams &P, const PixelMap &m, const Hit &best, LaneState &L) {
+    const CameraParams &C = P.cam;
+    const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
+    if (L.has_path) {
+        ++L.rays;
+        bool cont;
+        if (best.ref == kNoHit) {
+            L.sum_r += L.p.tr * C.background[0]; L.sum_g += L.p.tg * C.background[1]; L.sum_b += L.p.tb * C.background[2];
+            cont = false;   // camera.h:248
+        } else {
+            const Philox4 rnd = philox4x32_10(m.pixel, P.sample_begin + L.s, L.bounce + 1u, 0u, k0, k1);
+            cont = shade_hit(P.scene, best, rnd, L.ray, L.p, L.sum_r, L.sum_g, L.sum_b);
+            // ray_color(scattered, depth_left - 1): contributes nothing once depth_left hits 0 (camera.h:211-213)
+            if (cont && ++L.bounce == C.max_depth) cont = false;
+        }
+        if (!cont) {
+            L.has_path = false;
+            ++L.s;
+        }
+    }
+    if (!L.has_path) {
+        if (L.s == P.sample_count) return false;
+        const Philox4 rnd = philox4x32_10(m.pixel, P.sample_begin + L.s, 0u, 0u, k0, k1);
+        camera_ray(C, m.px, m.py, rnd, L.ray, L.p);
+        L.bounce = 0;
+        L.has_path = true;
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// path_megakernel_voted (variant 2, EXPERIMENT, not the default): every lane is always in one of
+// three states (at an interior node / at a leaf / needs shading + a new ray); each iteration the
+// warp votes and executes ONLY the step kind most lanes are waiting for.  Measured on C2 it raises
+// active threads per instruction from 12.7 to 14.4 of 32 but issues 16 % more instructions
+// (the groups equilibrate near one third each), so it is no faster than the plain loop below;
+// kept so the comparison in profiles/ can be reproduced.
+template <int STACK, bool COUNT>
+__global__ void __launch_bounds__(kPathBlock) path_megakernel_voted(const __grid_constant__ RenderParams P) {
+    const CameraParams &C = P.cam;
+    const PixelMap m = map_pixel(C);
+    LaneState L;
+    TraversalCounters ctr;
+    Trav T;
+    uint2 stack[STACK];
+    T.cur = kTravDone;
+    bool done = !(m.valid && C.max_depth > 0 && P.sample_count > 0);
+
+    while (true) {
+        const bool wantN = !done && trav_at_node(T);
+        const bool wantL = !done && trav_at_leaf(T);
+        const bool wantS = !done && trav_done(T);
+        const unsigned mN = __ballot_sync(0xffffffffu, wantN);
+        const unsigned mL = __ballot_sync(0xffffffffu, wantL);
+        const unsigned mS = __ballot_sync(0xffffffffu, wantS);
+        if (!(mN | mL | mS)) break;
+        const int cN = __popc(mN), cL = __popc(mL), cS = __popc(mS);
+        if (cN >= cL && cN >= cS) {
+            if (wantN) {
+                if (COUNT) ctr.nodes++;
+                trav_node_step(P.scene, T, stack);
+            }
+        } else if (cL >= cS) {
+            if (wantL) {
+                const uint32_t c = trav_leaf_step(P.scene, T, stack);
+                if (COUNT) ctr.prims += c;
+            }
+        } else {
+            if (wantS) {
+                if (shade_and_advance(P, m, T.best, L))
+                    trav_init(T, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001,   // camera.h:217
+                              __longlong_as_double(0x7ff0000000000000LL));
+                else
+                    done = true;
+            }
+        }
+    }
+    write_pixel_and_counters(P, m, L.sum_r, L.sum_g, L.sum_b, L.rays, COUNT, ctr);
+}
+
+// path_megakernel (variant 0, default): every lane runs traverse-then-shade in a loop and starts
+// its next sample as soon as a path ends.  64 registers (16 blocks = 32 warps per SM) measured
+// fastest on B200: 8/12/16/20/24 blocks per SM gave 2707/3171/3263/2630/2307 Mpaths/s on C2.
+template <int STACK, bool COUNT, int MINB = 16>
+__global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel(const __grid_constant__ RenderParams P) {
+    const CameraParams &C = P.cam;
+    const PixelMap m = map_pixel(C);
+    LaneState L;
+    TraversalCounters ctr;
+    Hit best{0.0, kNoHit};
+    if (m.valid && C.max_depth > 0 && P.sample_count > 0) {
+        while (shade_and_advance(P, m, best, L)) {
+            // world.hit_by(ray, Interval::with_min(0.00001))  (camera.h:217)
+            best = closest_hit<STACK, COUNT>(P.scene, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001,
+                                             __longlong_as_double(0x7ff0000000000000LL), &ctr);
+        }
+    }
+    write_pixel_and_counters(P, m, L.sum_r, L.sum_g, L.sum_b, L.rays, COUNT, ctr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -155,18 +237,23 @@ cudaError_t launch_raycast(int stack, const DeviceScene &S, const double *rays, 
 }
 
 template <int STACK>
-static cudaError_t launch_path_t(const RenderParams &P, bool count, cudaStream_t st) {
+static cudaError_t launch_path_t(const RenderParams &P, bool count, bool voted, cudaStream_t st) {
     const uint32_t tiles = ((P.cam.w + 7u) >> 3) * ((P.cam.h + 7u) >> 3);
     if (tiles == 0) return cudaSuccess;
-    if (count) path_megakernel<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
-    else path_megakernel<STACK, false><<<tiles, kPathBlock, 0, st>>>(P);
+    if (!voted) {
+        if (count) path_megakernel<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
+        else path_megakernel<STACK, false><<<tiles, kPathBlock, 0, st>>>(P);
+    } else {
+        if (count) path_megakernel_voted<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
+        else path_megakernel_voted<STACK, false><<<tiles, kPathBlock, 0, st>>>(P);
+    }
     return cudaGetLastError();
 }
 
-cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, cudaStream_t st) {
-    if (stack <= 32) return launch_path_t<32>(P, count, st);
-    if (stack <= 64) return launch_path_t<64>(P, count, st);
-    return launch_path_t<128>(P, count, st);
+cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool voted, cudaStream_t st) {
+    if (stack <= 32) return launch_path_t<32>(P, count, voted, st);
+    if (stack <= 64) return launch_path_t<64>(P, count, voted, st);
+    return launch_path_t<128>(P, count, voted, st);
 }
 
 cudaError_t launch_tonemap(const float *hdr, long long n_pixels, int32_t *out, int clamp, cudaStream_t st) {

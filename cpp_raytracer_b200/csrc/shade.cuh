@@ -21,10 +21,12 @@ struct CameraParams {
     uint32_t w, h, max_depth;
 };
 
+struct Ray {
+    double ox, oy, oz, dx, dy, dz;   // direction NOT normalised, as in the reference (ray3d.h)
+};
+
 struct PathState {
-    double ox, oy, oz, dx, dy, dz;
     float tr, tg, tb;   // throughput (product of attenuations so far)
-    float lr, lg, lb;   // radiance gathered so far along this path
 };
 
 // Uniform direction on the unit sphere from two uniforms (what random_unit_vector() produces
@@ -41,7 +43,7 @@ __device__ __forceinline__ void sample_unit_sphere(float u1, float u2, double &x
 
 // camera.h:184-200 (+ :160-168 for the defocus disk)
 __device__ __forceinline__ void camera_ray(const CameraParams &C, uint32_t px, uint32_t py, const Philox4 &rnd,
-                                           PathState &p) {
+                                           Ray &r, PathState &p) {
     double ox = C.center[0], oy = C.center[1], oz = C.center[2];
     if (C.defocus) {
         // uniform point in the unit disk (random_vector_in_unit_disk, vec3d.h:79-85)
@@ -58,16 +60,18 @@ __device__ __forceinline__ void camera_ray(const CameraParams &C, uint32_t px, u
     const double sx = ((C.pixel00[0] + row * C.delta_y[0]) + col * C.delta_x[0]) + jx * C.delta_x[0] + jy * C.delta_y[0];
     const double sy = ((C.pixel00[1] + row * C.delta_y[1]) + col * C.delta_x[1]) + jx * C.delta_x[1] + jy * C.delta_y[1];
     const double sz = ((C.pixel00[2] + row * C.delta_y[2]) + col * C.delta_x[2]) + jx * C.delta_x[2] + jy * C.delta_y[2];
-    p.ox = ox; p.oy = oy; p.oz = oz;
-    p.dx = sx - ox; p.dy = sy - oy; p.dz = sz - oz;   // NOT normalised (camera.h:199)
+    r.ox = ox; r.oy = oy; r.oz = oz;
+    r.dx = sx - ox; r.dy = sy - oy; r.dz = sz - oz;   // NOT normalised (camera.h:199)
     p.tr = p.tg = p.tb = 1.0f;
-    p.lr = p.lg = p.lb = 0.0f;
 }
 
-// Applies one surface interaction.  Returns true if the path continues with the new ray in `p`.
-__device__ __forceinline__ bool shade_hit(const DeviceScene &S, const Hit &h, const Philox4 &rnd, PathState &p) {
+// Applies one surface interaction.  Returns true if the path continues with the new ray in `r`.
+// Emitted light is added to (acc_r, acc_g, acc_b) weighted by the path throughput: the sum over a
+// path of throughput x emission is what ray_color's recursion returns (camera.h:233-234).
+__device__ __forceinline__ bool shade_hit(const DeviceScene &S, const Hit &h, const Philox4 &rnd, Ray &r, PathState &p,
+                                          float &acc_r, float &acc_g, float &acc_b) {
     // hit point: ray(t) = origin + t * dir (ray3d.h:16)
-    const double hx = p.ox + h.t * p.dx, hy = p.oy + h.t * p.dy, hz = p.oz + h.t * p.dz;
+    const double hx = r.ox + h.t * r.dx, hy = r.oy + h.t * r.dy, hz = r.oz + h.t * r.dz;
     double nx, ny, nz;
     uint32_t mat_id;
     if (h.ref & kQuadFlagD) {
@@ -82,13 +86,13 @@ __device__ __forceinline__ bool shade_hit(const DeviceScene &S, const Hit &h, co
         mat_id = __ldg(&S.sphere_meta[h.ref]).y;
     }
     // front/back face (hittable.h:56-70)
-    const bool inside = (p.dx * nx + p.dy * ny + p.dz * nz) > 0;
+    const bool inside = (r.dx * nx + r.dy * ny + r.dz * nz) > 0;
     if (inside) { nx = -nx; ny = -ny; nz = -nz; }
 
     const float4 m0 = __ldg((const float4 *)(S.materials + mat_id));
     const uint32_t kind = __float_as_uint(m0.w);
     if (kind == 3u) {   // DiffuseLight: emits on both faces, never scatters (material.h:248-263)
-        p.lr += p.tr * m0.x; p.lg += p.tg * m0.y; p.lb += p.tb * m0.z;
+        acc_r += p.tr * m0.x; acc_g += p.tg * m0.y; acc_b += p.tb * m0.z;
         return false;
     }
     double sx, sy, sz;
@@ -100,8 +104,8 @@ __device__ __forceinline__ bool shade_hit(const DeviceScene &S, const Hit &h, co
         p.tr *= m0.x; p.tg *= m0.y; p.tb *= m0.z;
     } else {
         // unit_vector(): *this / mag(), and operator/= multiplies by 1/d (vec3d.h:31,127-130)
-        const double inv_len = 1.0 / sqrt(p.dx * p.dx + p.dy * p.dy + p.dz * p.dz);
-        const double vx = p.dx * inv_len, vy = p.dy * inv_len, vz = p.dz * inv_len;
+        const double inv_len = 1.0 / sqrt(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
+        const double vx = r.dx * inv_len, vy = r.dy * inv_len, vz = r.dz * inv_len;
         const double vdotn = vx * nx + vy * ny + vz * nz;
         // reflected(v, n) = v - 2*dot(v,n)*n (vec3d.h:144-155)
         const double rx = vx - (2 * vdotn) * nx, ry = vy - (2 * vdotn) * ny, rz = vz - (2 * vdotn) * nz;
@@ -134,8 +138,8 @@ __device__ __forceinline__ bool shade_hit(const DeviceScene &S, const Hit &h, co
             // attenuation is (1,1,1) (material.h:217)
         }
     }
-    p.ox = hx; p.oy = hy; p.oz = hz;   // scattered ray starts AT the hit point (no offset; tmin = 1e-5 guards acne)
-    p.dx = sx; p.dy = sy; p.dz = sz;   // NOT normalised
+    r.ox = hx; r.oy = hy; r.oz = hz;   // scattered ray starts AT the hit point (no offset; tmin = 1e-5 guards acne)
+    r.dx = sx; r.dy = sy; r.dz = sz;   // NOT normalised
     return true;
 }
 

@@ -104,114 +104,143 @@ __device__ __forceinline__ bool quad_root(double ox, double oy, double oz, doubl
 
 #define B200RT_CSWAP(a, b) { const uint32_t lo_ = min(a, b); b = max(a, b); a = lo_; }
 
-template <int STACK, bool COUNT>
-__device__ __forceinline__ Hit closest_hit(const DeviceScene &S, double ox, double oy, double oz,
-                                           double dx, double dy, double dz, double tmin, double tmax,
-                                           TraversalCounters *ctr) {
-    // ---- per-ray setup for the FP32 box tests -------------------------------------------
-    const float fox = (float)ox, foy = (float)oy, foz = (float)oz;
+constexpr uint32_t kTravDone = 0xFFFFFFFFu;   // `cur` value once the stack has run dry
+
+// Per-ray traversal state.  The traversal is written as STEPS (one interior node, or one leaf)
+// so that kernels can either run them in a plain loop (closest_hit below) or let a warp vote
+// on which kind of step to execute next (path_megakernel).
+struct Trav {
+    double ox, oy, oz, dx, dy, dz;   // the ray, exactly as given (FP64; direction not normalised)
+    double a;                        // dot(dir, dir), hoisted out of Sphere::hit_by (sphere.h:49)
+    double tmin;
+    Hit best;                        // best.t doubles as the shrinking ray_times.max (bvh.h:651)
+    float fox, foy, foz, fix, fiy, fiz, eox, eoy, eoz;   // FP32 ray for box tests + per-axis pads
+    float tmin32, tmax32;
+    int nearx, neary, nearz;         // which float4 of a node is the near plane per axis
+    int sp;
+    uint32_t cur;                    // interior node index | leaf reference | kTravDone
+};
+
+__device__ __forceinline__ bool trav_at_node(const Trav &T) { return !(T.cur & kLeafFlagD); }
+__device__ __forceinline__ bool trav_at_leaf(const Trav &T) { return (T.cur & kLeafFlagD) && T.cur != kTravDone; }
+__device__ __forceinline__ bool trav_done(const Trav &T) { return T.cur == kTravDone; }
+
+__device__ __forceinline__ void trav_init(Trav &T, double ox, double oy, double oz, double dx, double dy, double dz,
+                                          double tmin, double tmax) {
+    T.ox = ox; T.oy = oy; T.oz = oz; T.dx = dx; T.dy = dy; T.dz = dz;
+    T.fox = (float)ox; T.foy = (float)oy; T.foz = (float)oz;
     // 1/d in FP32.  A zero component gives +-inf on purpose: (plane - o) * inf is -inf / +inf when
     // the origin is strictly inside / outside the slab and NaN when it lies exactly on the plane;
     // fmaxf/fminf drop NaN operands, i.e. "no constraint from this axis", which is the right
     // answer for a ray travelling inside a slab's boundary plane.  (The reference's own slab
     // test, aabb.h:132-174, mishandles -0.0 here; ours does not depend on the sign of zero.)
-    const float fix = (float)(1.0 / dx), fiy = (float)(1.0 / dy), fiz = (float)(1.0 / dz);
+    T.fix = (float)(1.0 / dx); T.fiy = (float)(1.0 / dy); T.fiz = (float)(1.0 / dz);
     // additive pad in t-space for the origin's rounding to FP32 (exact per ray, rounded up);
     // exactly representable origins need none (and must not produce 0 * inf).
-    const double rx = fabs(ox - (double)fox), ry = fabs(oy - (double)foy), rz = fabs(oz - (double)foz);
-    const float eox = rx == 0.0 ? 0.0f : __double2float_ru(rx * (double)fabsf(fix) * 1.00001);
-    const float eoy = ry == 0.0 ? 0.0f : __double2float_ru(ry * (double)fabsf(fiy) * 1.00001);
-    const float eoz = rz == 0.0 ? 0.0f : __double2float_ru(rz * (double)fabsf(fiz) * 1.00001);
-    // which float4 of the node holds the near plane on each axis (lo if dir >= 0, hi otherwise)
-    const int nearx = fix < 0.0f ? 1 : 0, neary = fiy < 0.0f ? 3 : 2, nearz = fiz < 0.0f ? 5 : 4;
-    const int farx = nearx ^ 1, fary = neary ^ 1, farz = nearz ^ 1;
-    const float tmin32 = __double2float_rd(tmin);
-    float tmax32 = __double2float_ru(tmax);
+    const double rx = fabs(ox - (double)T.fox), ry = fabs(oy - (double)T.foy), rz = fabs(oz - (double)T.foz);
+    T.eox = rx == 0.0 ? 0.0f : __double2float_ru(rx * (double)fabsf(T.fix) * 1.00001);
+    T.eoy = ry == 0.0 ? 0.0f : __double2float_ru(ry * (double)fabsf(T.fiy) * 1.00001);
+    T.eoz = rz == 0.0 ? 0.0f : __double2float_ru(rz * (double)fabsf(T.fiz) * 1.00001);
+    T.nearx = T.fix < 0.0f ? 1 : 0; T.neary = T.fiy < 0.0f ? 3 : 2; T.nearz = T.fiz < 0.0f ? 5 : 4;
+    T.tmin = tmin;
+    T.tmin32 = __double2float_rd(tmin);
+    T.tmax32 = __double2float_ru(tmax);
+    T.a = dx * dx + dy * dy + dz * dz;
+    T.best.t = tmax;
+    T.best.ref = kNoHit;
+    T.sp = 0;
+    T.cur = 0;   // root
+}
 
-    const double a = dx * dx + dy * dy + dz * dz;   // sphere.h:49
-
-    uint2 stack[STACK];
-    int sp = 0;
-    uint32_t cur = 0;   // root
-    Hit best{tmax, kNoHit};
-
-    while (true) {
-        if (!(cur & kLeafFlagD)) {
-            // ---------------- interior: test the four child boxes ------------------------
-            const float4 *n = S.nodes + (size_t)cur * 8;
-            const float4 bnx = __ldg(n + nearx), bfx = __ldg(n + farx);
-            const float4 bny = __ldg(n + neary), bfy = __ldg(n + fary);
-            const float4 bnz = __ldg(n + nearz), bfz = __ldg(n + farz);
-            const int4 ch = __ldg((const int4 *)(n + 6));
-            if (COUNT) ctr->nodes++;
-            const float tfar_cap = tmax32;
-#define B200RT_SLOT(c, k)                                                                                  \
-            uint32_t key##k;                                                                               \
-            {                                                                                              \
-                const float tn = fmaxf(fmaxf(__fmaf_rn(bnx.c - fox, fix, -eox), __fmaf_rn(bny.c - foy, fiy, -eoy)), \
-                                       fmaxf(__fmaf_rn(bnz.c - foz, fiz, -eoz), tmin32));                   \
-                const float tf = fminf(fminf(__fmaf_rn(bfx.c - fox, fix, eox), __fmaf_rn(bfy.c - foy, fiy, eoy)),   \
-                                       fminf(__fmaf_rn(bfz.c - foz, fiz, eoz), tfar_cap));                  \
-                key##k = (tn <= tf * kBoxSlack) ? ((__float_as_uint(tn) & ~3u) | k) : 0xFFFFFFFFu;          \
-            }
-            B200RT_SLOT(x, 0) B200RT_SLOT(y, 1) B200RT_SLOT(z, 2) B200RT_SLOT(w, 3)
-#undef B200RT_SLOT
-            // sort the four keys ascending (nearest first); misses sink to the end
-            B200RT_CSWAP(key0, key1) B200RT_CSWAP(key2, key3) B200RT_CSWAP(key0, key2)
-            B200RT_CSWAP(key1, key3) B200RT_CSWAP(key1, key2)
-#define B200RT_CHILD(key) ((uint32_t)(((key) & 3u) == 0 ? ch.x : ((key) & 3u) == 1 ? ch.y : ((key) & 3u) == 2 ? ch.z : ch.w))
-            if (key0 != 0xFFFFFFFFu) {
-                if (key3 != 0xFFFFFFFFu) stack[sp++] = make_uint2(B200RT_CHILD(key3), key3);
-                if (key2 != 0xFFFFFFFFu) stack[sp++] = make_uint2(B200RT_CHILD(key2), key2);
-                if (key1 != 0xFFFFFFFFu) stack[sp++] = make_uint2(B200RT_CHILD(key1), key1);
-                cur = B200RT_CHILD(key0);
-                continue;
-            }
-#undef B200RT_CHILD
-        } else {
-            // ---------------- leaf: FP64 primitive tests ----------------------------------
-            const uint32_t cnt = (cur >> 26) & 0xFu, first = cur & 0x03FFFFFFu;
-            if (cur & kQuadFlagD) {
-                for (uint32_t i = 0; i < cnt; ++i) {
-                    if (COUNT) ctr->prims++;
-                    double t;
-                    if (quad_root(ox, oy, oz, dx, dy, dz, S.quads + (size_t)(first + i) * 8, tmin, best.t,
-                                  best.ref != kNoHit, t)) {
-                        const uint32_t ref = kQuadFlagD | (first + i);
-                        if (t < best.t || canonical_prim(S, ref) < canonical_prim(S, best.ref)) {
-                            best.t = t;
-                            best.ref = ref;
-                            tmax32 = __double2float_ru(t);
-                        }
-                    }
-                }
-            } else {
-                for (uint32_t i = 0; i < cnt; ++i) {
-                    if (COUNT) ctr->prims++;
-                    const double2 s0 = __ldg(S.spheres + (size_t)(first + i) * 2);
-                    const double2 s1 = __ldg(S.spheres + (size_t)(first + i) * 2 + 1);
-                    double t;
-                    if (sphere_root(ox, oy, oz, dx, dy, dz, a, s0.x, s0.y, s1.x, s1.y, tmin, best.t,
-                                    best.ref != kNoHit, t)) {
-                        const uint32_t ref = first + i;
-                        if (t < best.t || canonical_prim(S, ref) < canonical_prim(S, best.ref)) {
-                            best.t = t;
-                            best.ref = ref;
-                            tmax32 = __double2float_ru(t);
-                        }
-                    }
-                }
-            }
-        }
-        // ---------------- pop, skipping entries that can no longer contain a closer hit -------
-        bool got = false;
-        while (sp > 0) {
-            const uint2 e = stack[--sp];
-            if (__uint_as_float(e.y & ~3u) <= tmax32 * kBoxSlack) { cur = e.x; got = true; break; }
-        }
-        if (!got) break;
+// Pops the next stack entry that can still contain a closer hit into T.cur (kTravDone if none).
+__device__ __forceinline__ void trav_pop(Trav &T, const uint2 *stack) {
+    T.cur = kTravDone;
+    while (T.sp > 0) {
+        const uint2 e = stack[--T.sp];
+        if (__uint_as_float(e.y & ~3u) <= T.tmax32 * kBoxSlack) { T.cur = e.x; break; }
     }
-    return best;
+}
+
+// One interior node: conservative FP32 slab tests of its four child boxes, nearest-first order.
+__device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, uint2 *stack) {
+    const float4 *n = S.nodes + (size_t)T.cur * 8;
+    const float4 bnx = __ldg(n + T.nearx), bfx = __ldg(n + (T.nearx ^ 1));
+    const float4 bny = __ldg(n + T.neary), bfy = __ldg(n + (T.neary ^ 1));
+    const float4 bnz = __ldg(n + T.nearz), bfz = __ldg(n + (T.nearz ^ 1));
+    const int4 ch = __ldg((const int4 *)(n + 6));
+#define B200RT_SLOT(c, k)                                                                                        \
+    uint32_t key##k;                                                                                             \
+    {                                                                                                            \
+        const float tn = fmaxf(fmaxf(__fmaf_rn(bnx.c - T.fox, T.fix, -T.eox), __fmaf_rn(bny.c - T.foy, T.fiy, -T.eoy)), \
+                               fmaxf(__fmaf_rn(bnz.c - T.foz, T.fiz, -T.eoz), T.tmin32));                         \
+        const float tf = fminf(fminf(__fmaf_rn(bfx.c - T.fox, T.fix, T.eox), __fmaf_rn(bfy.c - T.foy, T.fiy, T.eoy)),   \
+                               fminf(__fmaf_rn(bfz.c - T.foz, T.fiz, T.eoz), T.tmax32));                          \
+        key##k = (tn <= tf * kBoxSlack) ? ((__float_as_uint(tn) & ~3u) | k) : 0xFFFFFFFFu;                        \
+    }
+    B200RT_SLOT(x, 0) B200RT_SLOT(y, 1) B200RT_SLOT(z, 2) B200RT_SLOT(w, 3)
+#undef B200RT_SLOT
+    // sort the four keys ascending (nearest first); misses sink to the end
+    B200RT_CSWAP(key0, key1) B200RT_CSWAP(key2, key3) B200RT_CSWAP(key0, key2)
+    B200RT_CSWAP(key1, key3) B200RT_CSWAP(key1, key2)
+#define B200RT_CHILD(key) ((uint32_t)(((key) & 3u) == 0 ? ch.x : ((key) & 3u) == 1 ? ch.y : ((key) & 3u) == 2 ? ch.z : ch.w))
+    if (key0 != 0xFFFFFFFFu) {
+        if (key3 != 0xFFFFFFFFu) stack[T.sp++] = make_uint2(B200RT_CHILD(key3), key3);
+        if (key2 != 0xFFFFFFFFu) stack[T.sp++] = make_uint2(B200RT_CHILD(key2), key2);
+        if (key1 != 0xFFFFFFFFu) stack[T.sp++] = make_uint2(B200RT_CHILD(key1), key1);
+        T.cur = B200RT_CHILD(key0);
+    } else {
+        trav_pop(T, stack);
+    }
+#undef B200RT_CHILD
+}
+
+// One leaf: FP64 primitive tests in the reference's arithmetic, then pop.
+__device__ __forceinline__ uint32_t trav_leaf_step(const DeviceScene &S, Trav &T, const uint2 *stack) {
+    const uint32_t cnt = (T.cur >> 26) & 0xFu, first = T.cur & 0x03FFFFFFu;
+    const bool is_quad = T.cur & kQuadFlagD;
+    for (uint32_t i = 0; i < cnt; ++i) {
+        double t;
+        bool hit;
+        uint32_t ref;
+        if (is_quad) {
+            ref = kQuadFlagD | (first + i);
+            hit = quad_root(T.ox, T.oy, T.oz, T.dx, T.dy, T.dz, S.quads + (size_t)(first + i) * 8, T.tmin, T.best.t,
+                            T.best.ref != kNoHit, t);
+        } else {
+            ref = first + i;
+            const double2 s0 = __ldg(S.spheres + (size_t)(first + i) * 2);
+            const double2 s1 = __ldg(S.spheres + (size_t)(first + i) * 2 + 1);
+            hit = sphere_root(T.ox, T.oy, T.oz, T.dx, T.dy, T.dz, T.a, s0.x, s0.y, s1.x, s1.y, T.tmin, T.best.t,
+                              T.best.ref != kNoHit, t);
+        }
+        // strictly closer wins; an exact tie goes to the lower canonical index (scene.h:59-75)
+        if (hit && (t < T.best.t || canonical_prim(S, ref) < canonical_prim(S, T.best.ref))) {
+            T.best.t = t;
+            T.best.ref = ref;
+            T.tmax32 = __double2float_ru(t);
+        }
+    }
+    trav_pop(T, stack);
+    return cnt;
+}
+
+template <int STACK, bool COUNT>
+__device__ __forceinline__ Hit closest_hit(const DeviceScene &S, double ox, double oy, double oz,
+                                           double dx, double dy, double dz, double tmin, double tmax,
+                                           TraversalCounters *ctr) {
+    Trav T;
+    uint2 stack[STACK];
+    trav_init(T, ox, oy, oz, dx, dy, dz, tmin, tmax);
+    while (!trav_done(T)) {
+        if (trav_at_node(T)) {
+            if (COUNT) ctr->nodes++;
+            trav_node_step(S, T, stack);
+        } else {
+            const uint32_t c = trav_leaf_step(S, T, stack);
+            if (COUNT) ctr->prims += c;
+        }
+    }
+    return T.best;
 }
 
 }  // namespace b200rt

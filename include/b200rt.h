@@ -97,7 +97,11 @@ typedef struct B200rtSceneInfo {
     double build_ms, upload_ms;
 } B200rtSceneInfo;
 
-enum { B200RT_VARIANT_MEGAKERNEL = 0, B200RT_VARIANT_WAVEFRONT = 1 };
+enum {
+    B200RT_VARIANT_MEGAKERNEL = 0,          /* one thread per pixel, path regeneration (default) */
+    B200RT_VARIANT_WAVEFRONT = 1,           /* per-material ray queues */
+    B200RT_VARIANT_MEGAKERNEL_VOTED = 2     /* experiment: warp-voted node/leaf/shade step scheduling */
+};
 enum {
     B200RT_FLAG_SUM = 1,          /* write the per-pixel SUM over the samples of this call instead of the mean */
     B200RT_FLAG_ACCUMULATE = 2,   /* device entry only: add into the output buffer instead of overwriting */

