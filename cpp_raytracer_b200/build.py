@@ -30,6 +30,29 @@ NVCC_FLAGS = [
 ]
 
 
+HOST_DIR = os.path.join(HERE, "host")
+HOST_BIN = os.path.join(HOST_DIR, "b200rt_scenes")
+HOST_DEPS = ["scenes_main.cpp", "scenes.hpp", os.path.join("include", "b200rt", "raytracer.hpp")]
+
+
+def build_host(force: bool = False) -> str:
+    """Builds host/b200rt_scenes: the reference's scene set written against the API-compatible
+    C++ headers (host/include), linked against libb200rt.so."""
+    deps = [os.path.join(HOST_DIR, d) for d in HOST_DEPS] + [LIB]
+    if not force and os.path.exists(HOST_BIN) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_BIN) for d in deps):
+        return HOST_BIN
+    cmd = ["g++", "-std=c++20", "-O2", "-ffp-contract=off", "-I" + os.path.join(HOST_DIR, "include"),
+           "-o", HOST_BIN, os.path.join(HOST_DIR, "scenes_main.cpp"), "-L" + HERE, "-lb200rt", "-Wl,-rpath,$ORIGIN/.."]
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building host/b200rt_scenes")
+    return HOST_BIN
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
@@ -63,3 +86,4 @@ if __name__ == "__main__":
     ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args()
     print(build(force=a.force, verbose=a.verbose))
+    print(build_host(force=a.force))

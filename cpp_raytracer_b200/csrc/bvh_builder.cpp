@@ -5,6 +5,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -17,16 +20,17 @@ namespace {
 constexpr double kInf = std::numeric_limits<double>::infinity();
 
 inline Box3 empty_box() { return Box3{{kInf, kInf, kInf}, {-kInf, -kInf, -kInf}}; }
+// (primitive boxes never hold NaN: plain compares are enough and much cheaper than fmin/fmax)
 inline void grow(Box3 &b, const Box3 &o) {
     for (int a = 0; a < 3; ++a) {
-        b.lo[a] = std::fmin(b.lo[a], o.lo[a]);
-        b.hi[a] = std::fmax(b.hi[a], o.hi[a]);
+        b.lo[a] = o.lo[a] < b.lo[a] ? o.lo[a] : b.lo[a];
+        b.hi[a] = o.hi[a] > b.hi[a] ? o.hi[a] : b.hi[a];
     }
 }
 inline void grow_point(Box3 &b, const double p[3]) {
     for (int a = 0; a < 3; ++a) {
-        b.lo[a] = std::fmin(b.lo[a], p[a]);
-        b.hi[a] = std::fmax(b.hi[a], p[a]);
+        b.lo[a] = p[a] < b.lo[a] ? p[a] : b.lo[a];
+        b.hi[a] = p[a] > b.hi[a] ? p[a] : b.hi[a];
     }
 }
 inline void centroid(const Box3 &b, double c[3]) {
@@ -110,17 +114,17 @@ struct Builder {
         return r;
     }
 
-    struct Bin {
-        Box3 box = empty_box();
-        double weight = 0;
-        uint32_t count = 0;
+    struct Bin {   // trivially constructible on purpose: only the 3*B bins in use are reset
+        Box3 box;
+        double weight;
+        uint32_t count;
+        void reset() { box = empty_box(); weight = 0; count = 0; }
     };
-    inline int bin_of(double c, double cmin, double inv_extent) const {
+    static inline int bin_of(double c, double cmin, double inv_extent, int B) {
         int b = (int)((c - cmin) * inv_extent);
-        return b < 0 ? 0 : (b >= P.sah_bins ? P.sah_bins - 1 : b);
+        return b < 0 ? 0 : (b >= B ? B - 1 : b);
     }
-    void bin_chunk(uint32_t lo, uint32_t hi, const RangeInfo &info, const double inv_ext[3], Bin *bins /*3*B*/) const {
-        const int B = P.sah_bins;
+    void bin_chunk(uint32_t lo, uint32_t hi, const RangeInfo &info, const double inv_ext[3], Bin *bins /*3*B*/, int B) const {
         for (uint32_t i = lo; i < hi; ++i) {
             const uint32_t prim = idx[i];
             const Box3 &b = boxes[prim];
@@ -129,7 +133,7 @@ struct Builder {
             const double w = cost_of(type_of(prim));
             for (int a = 0; a < 3; ++a) {
                 if (inv_ext[a] == 0) continue;
-                Bin &bn = bins[a * B + bin_of(c[a], info.cbox.lo[a], inv_ext[a])];
+                Bin &bn = bins[a * B + bin_of(c[a], info.cbox.lo[a], inv_ext[a], B)];
                 grow(bn.box, b);
                 bn.weight += w;
                 bn.count++;
@@ -168,18 +172,21 @@ struct Builder {
         const bool depth_exhausted = depth + ceil_log2(n) >= P.max_binary_depth;
 
         if (!depth_exhausted && max_ext > 0 && std::isfinite(max_ext)) {
-            const int B = P.sah_bins;
+            // fewer bins for small ranges: clearing 3 x 32 bins per node would dominate the build
+            const int B = n >= 64u ? P.sah_bins : (n >= 16u ? std::min(P.sah_bins, 16) : std::min(P.sah_bins, 8));
             double inv_ext[3];
             for (int a = 0; a < 3; ++a) inv_ext[a] = (ext[a] > 0 && std::isfinite(ext[a])) ? B / ext[a] : 0.0;
             Bin bins[3 * kMaxBins];
+            for (int k = 0; k < 3 * B; ++k) bins[k].reset();
             if (!pool) {
-                bin_chunk(lo, hi, info, inv_ext, bins);
+                bin_chunk(lo, hi, info, inv_ext, bins, B);
             } else {
                 const int chunks = pool->size() * 2;
                 std::vector<std::vector<Bin>> part(chunks, std::vector<Bin>(3 * B));
                 pool->parallel_for(chunks, [&](int c) {
+                    for (auto &b : part[c]) b.reset();
                     bin_chunk(lo + (uint32_t)((uint64_t)n * c / chunks), lo + (uint32_t)((uint64_t)n * (c + 1) / chunks),
-                              info, inv_ext, part[c].data());
+                              info, inv_ext, part[c].data(), B);
                 });
                 for (auto &p : part)
                     for (int k = 0; k < 3 * B; ++k) {
@@ -232,7 +239,7 @@ struct Builder {
                 const double cmin = info.cbox.lo[best_axis], ie = inv_ext[best_axis];
                 auto it = std::partition(idx.begin() + lo, idx.begin() + hi, [&](uint32_t prim) {
                     const Box3 &b = boxes[prim];
-                    return bin_of(0.5 * b.lo[best_axis] + 0.5 * b.hi[best_axis], cmin, ie) <= best_bin;
+                    return bin_of(0.5 * b.lo[best_axis] + 0.5 * b.hi[best_axis], cmin, ie, B) <= best_bin;
                 });
                 mid = (uint32_t)(it - idx.begin());
                 have_split = mid > lo && mid < hi;
@@ -388,10 +395,12 @@ bool build_bvh4(const std::vector<Box3> &prim_boxes, uint64_t n_spheres, uint64_
     for (uint64_t i = 0; i < n; ++i) B.idx[i] = (uint32_t)i;
     B.nodes.resize(2 * n);
     B.n_nodes = 1;
+    const auto t_start = std::chrono::steady_clock::now();
     {
         ThreadPool pool(n < Builder::kTopRange ? 1 : threads);
         B.build(pool, (uint32_t)n);
     }
+    const auto t_built = std::chrono::steady_clock::now();
     out.binary_depth = B.max_depth.load();
 
     out.nodes.reserve(n / 2 + 16);
@@ -413,6 +422,12 @@ bool build_bvh4(const std::vector<Box3> &prim_boxes, uint64_t n_spheres, uint64_
         out.depth = C.max_depth4;
     }
     if (out.sphere_order.size() != n_spheres || out.quad_order.size() != n_quads) { *err = "internal: leaf order size mismatch"; return false; }
+    if (std::getenv("B200RT_BUILD_TIMING")) {
+        const auto t_end = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[b200rt] bvh build: binary tree %.1f ms (%d threads), collapse+emit %.1f ms, %zu nodes\n",
+                     std::chrono::duration<double, std::milli>(t_built - t_start).count(), threads,
+                     std::chrono::duration<double, std::milli>(t_end - t_built).count(), out.nodes.size());
+    }
     return true;
 }
 

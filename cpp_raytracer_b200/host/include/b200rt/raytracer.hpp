@@ -1,0 +1,510 @@
+// raytracer.hpp -- host-side C++ mirror of the reference's scene / camera / material API,
+// sitting on top of the C ABI (include/b200rt.h).
+//
+// A program written against DeltaPavonis/cpp_raytracer -- build a `Scene` out of `Sphere`,
+// `Parallelogram` and `Box` objects holding `Lambertian` / `Metal` / `Dielectric` /
+// `DiffuseLight` materials, configure a `Camera` with the fluent setters and call
+// `.render(world).send_as_ppm(path)` (reference src/main.cpp:13-650) -- compiles against this
+// header unchanged (the compatibility headers base/*.h, shapes/*.h, util/*.h, math/*.h next to
+// this directory forward here).  Same names, same argument meaning, same defaults, same error
+// convention (message on std::cout, then std::exit(-1); reference image.h:39-42, rgb.h:136-141).
+//
+// What is different by design: objects here only DESCRIBE the scene.  There is no CPU
+// intersection or shading code in this header: `Camera::render` flattens the scene into the flat
+// arrays of B200rtSceneDesc and calls b200rt_render_scene, i.e. the CUDA path.  Unknown
+// `Hittable` / `Material` subclasses are an error (closed set), never silently skipped.
+//
+// Reference lines each piece follows are cited inline.
+#pragma once
+
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include <fstream>
+#include <iostream>
+#include <memory>
+#include <mutex>
+#include <numbers>
+#include <optional>
+#include <random>
+#include <span>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../../../include/b200rt.h"
+
+// ===== util/rand_util.h ====================================================================
+// Bit-exact restatement of the reference's generators (rand_util.h:11-127): scenes are built
+// with these, so a scene function gives the same spheres here as in the reference.
+class SeedSeqGenerator {
+    using seed_type = uint32_t;
+    std::optional<seed_type> custom_seed;
+    std::mutex mtx;
+    SeedSeqGenerator() = default;
+public:
+    static SeedSeqGenerator &get_instance() { static SeedSeqGenerator s; return s; }
+    SeedSeqGenerator(const SeedSeqGenerator &) = delete;
+    SeedSeqGenerator &operator=(const SeedSeqGenerator &) = delete;
+    seed_type next_seed() {                                           // rand_util.h:51-69
+        std::lock_guard<std::mutex> g(mtx);
+        if (!custom_seed) {
+            custom_seed = std::random_device{}();
+            std::cout << "SeedSeqGenerator: No random seed provided, using " << *custom_seed
+                      << " (Use SeedSeqGenerator::get_instance().set_seed([custom seed]) to set a custom seed)" << std::endl;
+        }
+        custom_seed = 2'483'477u * (*custom_seed) + 2'987'434'823u;
+        return *custom_seed;
+    }
+    void set_seed(seed_type seed) {                                   // rand_util.h:75-79
+        std::cout << "SeedSeqGenerator: Using user-provided random seed " << seed << '\n' << std::endl;
+        custom_seed = seed;
+    }
+};
+
+inline double rand_double(double min = 0, double max = 1) {          // rand_util.h:85-117
+    thread_local uint32_t seed = SeedSeqGenerator::get_instance().next_seed();
+    seed = 1'664'525u * seed + 1'013'904'223u;
+    constexpr double SCALE = 1 / static_cast<double>(std::numeric_limits<uint32_t>::max() - 1);
+    return min + (max - min) * static_cast<double>(seed) * SCALE;
+}
+
+inline int rand_int(int min = 0, int max = 1) {                      // rand_util.h:120-127
+    thread_local std::mt19937 generator{SeedSeqGenerator::get_instance().next_seed()};
+    thread_local std::uniform_int_distribution<> dist;
+    dist.param(std::uniform_int_distribution<>::param_type{min, max});
+    return dist(generator);
+}
+
+// ===== math/interval.h (the parts scene code can touch) ====================================
+struct Interval {
+    double min, max;
+    Interval(double min_, double max_) : min{min_}, max{max_} {}
+    bool contains_inclusive(double d) const { return min <= d && d <= max; }
+    bool contains_exclusive(double d) const { return min < d && d < max; }
+    double size() const { return max - min; }
+    static Interval with_min(double m) { return Interval(m, std::numeric_limits<double>::infinity()); }
+};
+
+// ===== math/vec3d.h ==========================================================================
+struct Vec3D {
+    double x = 0, y = 0, z = 0;                                       // aggregate, as in the reference
+    const double &operator[](size_t a) const { return a == 0 ? x : (a == 1 ? y : z); }
+    double &operator[](size_t a) { return a == 0 ? x : (a == 1 ? y : z); }
+    Vec3D operator-() const { return Vec3D{-x, -y, -z}; }
+    Vec3D &operator+=(const Vec3D &r) { x += r.x; y += r.y; z += r.z; return *this; }
+    Vec3D &operator-=(const Vec3D &r) { x -= r.x; y -= r.y; z -= r.z; return *this; }
+    Vec3D &operator*=(double d) { x *= d; y *= d; z *= d; return *this; }
+    Vec3D &operator/=(double d) { return *this *= (1 / d); }         // vec3d.h:31
+    double mag() const { return std::sqrt(x * x + y * y + z * z); }
+    double mag_squared() const { return x * x + y * y + z * z; }
+    Vec3D unit_vector() const;
+    bool near_zero(double eps = 1e-8) const { return std::fabs(x) < eps && std::fabs(y) < eps && std::fabs(z) < eps; }
+    static Vec3D zero() { return Vec3D{0, 0, 0}; }
+    static Vec3D random(double min = 0, double max = 1) {            // braced list: x, y, z in order (vec3d.h:60)
+        return Vec3D{rand_double(min, max), rand_double(min, max), rand_double(min, max)};
+    }
+};
+inline Vec3D operator+(const Vec3D &a, const Vec3D &b) { auto r = a; r += b; return r; }
+inline Vec3D operator-(const Vec3D &a, const Vec3D &b) { auto r = a; r -= b; return r; }
+inline Vec3D operator*(const Vec3D &a, double d) { auto r = a; r *= d; return r; }
+inline Vec3D operator*(double d, const Vec3D &a) { return a * d; }
+inline Vec3D operator/(const Vec3D &a, double d) { auto r = a; r /= d; return r; }
+inline double dot(const Vec3D &a, const Vec3D &b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline Vec3D cross(const Vec3D &a, const Vec3D &b) {
+    return Vec3D{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+inline Vec3D Vec3D::unit_vector() const { return *this / this->mag(); }
+inline std::ostream &operator<<(std::ostream &os, const Vec3D &v) { return os << "(" << v.x << ", " << v.y << ", " << v.z << ")"; }
+using Point3D = Vec3D;
+
+struct Ray3D {                                                        // math/ray3d.h
+    Point3D origin{0, 0, 0};
+    Vec3D dir{0, 0, 0};
+    Point3D operator()(double t) const { return origin + t * dir; }
+};
+
+// ===== util/rgb.h =============================================================================
+class RGB {
+    RGB(double r_, double g_, double b_) : r{r_}, g{g_}, b{b_} {}
+public:
+    double r, g, b;
+    double luminance() const { return 0.2126 * r + 0.7152 * g + 0.0722 * b; }                 // rgb.h:28-30
+    static RGB from_mag(double red, double green, double blue) { return RGB(red, green, blue); }
+    static RGB from_mag(double v) { return from_mag(v, v, v); }
+    static RGB from_rgb(double red, double green, double blue, double max_magnitude = 255) {
+        return RGB(red / max_magnitude, green / max_magnitude, blue / max_magnitude);
+    }
+    static RGB from_rgb(double v, double max_magnitude = 255) { return from_rgb(v, v, v, max_magnitude); }
+    static RGB zero() { return from_mag(0); }
+    // rgb.h:64-66 passes three rand_double() calls as function ARGUMENTS, whose evaluation order
+    // is unspecified; g++ (the compiler the reference is built with) evaluates them last to first.
+    // The order is made explicit here so that scenes come out identical with any compiler; the
+    // scene-dump test pins it against reference-built scenes.
+    static RGB random(double min = 0, double max = 1) {
+        const double blue = rand_double(min, max);
+        const double green = rand_double(min, max);
+        const double red = rand_double(min, max);
+        return from_mag(red, green, blue);
+    }
+    RGB &operator+=(const RGB &o) { r += o.r; g += o.g; b += o.b; return *this; }
+    RGB &operator*=(double d) { r *= d; g *= d; b *= d; return *this; }
+    RGB &operator/=(double d) { return *this *= (1 / d); }
+    // rgb.h:90-113: Reinhard by luminance, gamma, int(scale * v); no clamp.
+    std::string as_string(std::string delimiter = " ", std::string surrounding = "", double max_magnitude = 255,
+                          double gamma = 2, bool use_tone_mapping = true) const {
+        double r2 = r, g2 = g, b2 = b;
+        if (use_tone_mapping) { const double L = luminance(); r2 /= 1 + L; g2 /= 1 + L; b2 /= 1 + L; }
+        const double scale = max_magnitude + 0.999999;
+        auto enc = [&](double v) { return std::to_string(static_cast<int>(scale * std::pow(v, 1 / gamma))); };
+        return (surrounding.empty() ? "" : std::string{surrounding[0]}) + enc(r2) + delimiter + enc(g2) + delimiter + enc(b2) +
+               (surrounding.empty() ? "" : std::string{surrounding[1]});
+    }
+};
+inline RGB operator+(const RGB &a, const RGB &b) { return RGB::from_mag(a.r + b.r, a.g + b.g, a.b + b.b); }
+inline RGB operator*(const RGB &a, double d) { auto r = a; r *= d; return r; }
+inline RGB operator*(double d, const RGB &a) { return a * d; }
+inline RGB operator*(const RGB &a, const RGB &b) { return RGB::from_mag(a.r * b.r, a.g * b.g, a.b * b.b); }
+inline RGB lerp(const RGB &a, const RGB &b, double d) {                                         // rgb.h:133-148
+    if (!Interval(0, 1).contains_inclusive(d)) {
+        std::cout << "Error: In `lerp(...)`, lerp proportion " << d << " is not in the range [0, 1]." << std::endl;
+        std::exit(-1);
+    }
+    return RGB::from_mag((1 - d) * a.r + d * b.r, (1 - d) * a.g + d * b.g, (1 - d) * a.b + d * b.b);
+}
+
+// ===== base/material.h ========================================================================
+// Parameter holders.  kind()/colour()/param() are what the flattening step reads.
+struct Material {
+    virtual int kind() const = 0;                  // B200RT_MAT_*
+    virtual RGB colour() const = 0;
+    virtual double param() const = 0;
+    virtual RGB emit() const { return RGB::zero(); }                                            // material.h:38-40
+    virtual void print_to(std::ostream &os) const = 0;
+    virtual ~Material() = default;
+};
+inline std::ostream &operator<<(std::ostream &os, const Material &m) { m.print_to(os); return os; }
+
+class Lambertian : public Material {                                                            // material.h:58-95
+    RGB intrinsic_color;
+public:
+    Lambertian(const RGB &c) : intrinsic_color{c} {}
+    int kind() const override { return B200RT_MAT_LAMBERTIAN; }
+    RGB colour() const override { return intrinsic_color; }
+    double param() const override { return 0; }
+    void print_to(std::ostream &os) const override { os << "Lambertian {color: " << intrinsic_color.as_string(", ", "()") << "} " << std::flush; }
+};
+class Metal : public Material {                                                                 // material.h:105-152
+    RGB intrinsic_color;
+    double fuzz_factor;
+public:
+    Metal(const RGB &c, double fuzz = 0) : intrinsic_color{c}, fuzz_factor{std::fmin(fuzz, 1.)} {}
+    int kind() const override { return B200RT_MAT_METAL; }
+    RGB colour() const override { return intrinsic_color; }
+    double param() const override { return fuzz_factor; }
+    void print_to(std::ostream &os) const override {
+        os << "Metal {color: " << intrinsic_color.as_string(", ", "()") << ", fuzz factor: " << fuzz_factor << "} " << std::flush;
+    }
+};
+class Dielectric : public Material {                                                            // material.h:164-227
+    double refr_index;
+public:
+    Dielectric(double refractive_index) : refr_index{refractive_index} {}
+    int kind() const override { return B200RT_MAT_DIELECTRIC; }
+    RGB colour() const override { return RGB::from_mag(1, 1, 1); }
+    double param() const override { return refr_index; }
+    void print_to(std::ostream &os) const override { os << "Dielectric {refractive index: " << refr_index << "} " << std::flush; }
+};
+class DiffuseLight : public Material {                                                          // material.h:231-275
+    RGB intrinsic_color;
+    double intensity;
+public:
+    DiffuseLight(const RGB &c, double intensity_) : intrinsic_color{c}, intensity{intensity_} {}
+    int kind() const override { return B200RT_MAT_LIGHT; }
+    RGB colour() const override { return intrinsic_color; }
+    double param() const override { return intensity; }
+    RGB emit() const override { return intensity * intrinsic_color; }
+    void print_to(std::ostream &os) const override {
+        os << "DiffuseLight {color: " << intrinsic_color.as_string(", ", "()") << ", intensity: " << intensity << "} " << std::flush;
+    }
+};
+
+// ===== base/hittable.h, shapes/*, base/scene.h ================================================
+struct Hittable {
+    // Compound objects return their parts; primitives return {} (hittable.h:112-117).
+    virtual std::vector<std::shared_ptr<Hittable>> get_primitive_components() const { return {}; }
+    virtual void print_to(std::ostream &os) const = 0;
+    virtual ~Hittable() = default;
+};
+inline std::ostream &operator<<(std::ostream &os, const Hittable &h) { h.print_to(os); return os; }
+
+struct Sphere : public Hittable {                                                               // sphere.h:16-22,112
+    Point3D center;
+    double radius;
+    std::shared_ptr<Material> material;
+    Sphere(const Point3D &center_, double radius_, std::shared_ptr<Material> material_)
+        : center{center_}, radius{radius_}, material{std::move(material_)} {}
+    void print_to(std::ostream &os) const override {
+        os << "Sphere {center: " << center << ", radius: " << radius << ", material: " << *material << "} " << std::flush;
+    }
+};
+
+class Parallelogram : public Hittable {                                                         // parallelogram.h:14-48,269
+    Point3D vertex;
+    Vec3D side1, side2;
+    std::shared_ptr<Material> material;
+public:
+    Parallelogram(const Point3D &vertex_, const Vec3D &side1_, const Vec3D &side2_, std::shared_ptr<Material> material_)
+        : vertex{vertex_}, side1{side1_}, side2{side2_}, material{std::move(material_)} {}
+    const Point3D &get_vertex() const { return vertex; }
+    const Vec3D &get_side1() const { return side1; }
+    const Vec3D &get_side2() const { return side2; }
+    const std::shared_ptr<Material> &get_material() const { return material; }
+    void print_to(std::ostream &os) const override {
+        os << "Parallelogram {vertex: " << vertex << ", side 1 vector: " << side1 << ", side 2 vector: " << side2 << " } " << std::flush;
+    }
+};
+
+class Scene : public Hittable {                                                                 // scene.h:12-125
+    std::vector<std::shared_ptr<Hittable>> objects;
+public:
+    operator auto &() { return objects; }
+    operator const auto &() const { return objects; }
+    auto size() const { return objects.size(); }
+    void clear() { objects.clear(); }
+    auto &operator[](size_t i) { return objects[i]; }
+    const auto &operator[](size_t i) const { return objects[i]; }
+    auto begin() { return objects.begin(); }
+    auto begin() const { return objects.cbegin(); }
+    auto end() { return objects.end(); }
+    auto end() const { return objects.cend(); }
+    void add(std::shared_ptr<Hittable> object) { objects.push_back(std::move(object)); }
+    void add(const Scene &scene) { for (const auto &o : scene) add(o); }
+    // scene.h:85-105: compounds expanded in place, primitives kept, insertion order preserved.
+    std::vector<std::shared_ptr<Hittable>> get_primitive_components() const override {
+        std::vector<std::shared_ptr<Hittable>> ret;
+        for (const auto &obj : objects) {
+            if (auto parts = obj->get_primitive_components(); !parts.empty())
+                ret.insert(ret.end(), std::make_move_iterator(parts.begin()), std::make_move_iterator(parts.end()));
+            else
+                ret.push_back(obj);
+        }
+        return ret;
+    }
+    void print_to(std::ostream &os) const override {
+        os << "Scene with " << size() << " objects:\n";
+        for (const auto &o : objects) { o->print_to(os); os << '\n'; }
+        os << std::flush;
+    }
+    Scene() = default;
+    Scene(std::span<const std::shared_ptr<Hittable>> objs) { for (const auto &o : objs) add(o); }
+};
+
+class Box : public Hittable {                                                                   // box.h:53-84
+    Scene faces;
+    std::shared_ptr<Material> material;
+public:
+    Box(const Point3D &vertex, const Point3D &opposite_vertex, std::shared_ptr<Material> material_) : material{std::move(material_)} {
+        Point3D lo, hi;
+        for (int i = 0; i < 3; ++i) { lo[i] = std::fmin(vertex[i], opposite_vertex[i]); hi[i] = std::fmax(vertex[i], opposite_vertex[i]); }
+        const Vec3D sx{hi.x - lo.x, 0, 0}, sy{0, hi.y - lo.y, 0}, sz{0, 0, hi.z - lo.z};
+        faces.add(std::make_shared<Parallelogram>(lo, sx, sy, material));
+        faces.add(std::make_shared<Parallelogram>(lo, sx, sz, material));
+        faces.add(std::make_shared<Parallelogram>(lo, sy, sz, material));
+        faces.add(std::make_shared<Parallelogram>(hi, -sx, -sy, material));
+        faces.add(std::make_shared<Parallelogram>(hi, -sx, -sz, material));
+        faces.add(std::make_shared<Parallelogram>(hi, -sy, -sz, material));
+    }
+    std::vector<std::shared_ptr<Hittable>> get_primitive_components() const override { return faces.get_primitive_components(); }
+    void print_to(std::ostream &os) const override { os << "Box {faces: " << faces << "} " << std::flush; }
+};
+
+// ===== util/image.h ===========================================================================
+class Image {
+    size_t w, h;
+    std::vector<std::vector<RGB>> pixels;
+    Image(size_t w_, size_t h_) : w{w_}, h{h_}, pixels(h_, std::vector<RGB>(w_, RGB::zero())) {}
+public:
+    auto width() const { return w; }
+    auto height() const { return h; }
+    auto &operator[](size_t row) { return pixels[row]; }
+    const auto &operator[](size_t row) const { return pixels[row]; }
+    double aspect_ratio() const { return static_cast<double>(w) / static_cast<double>(h); }
+    static Image with_dimensions(size_t width, size_t height) { return Image(width, height); }
+    // image.h:38-56: ASCII P3, one "r g b" line per pixel through RGB::as_string() defaults.
+    // The integers come from the tone-map kernel (b200rt_tonemap), formatting stays on the host.
+    void send_as_ppm(const std::string &destination) const {
+        std::ofstream fout(destination);
+        if (!fout.is_open()) {
+            std::cout << "Error: In Image::print_as_ppm(), could not open the file \"" << destination << "\"" << std::endl;
+            std::exit(-1);
+        }
+        std::vector<float> hdr(w * h * 3);
+        for (size_t r = 0; r < h; ++r)
+            for (size_t c = 0; c < w; ++c) {
+                hdr[(r * w + c) * 3 + 0] = (float)pixels[r][c].r;
+                hdr[(r * w + c) * 3 + 1] = (float)pixels[r][c].g;
+                hdr[(r * w + c) * 3 + 2] = (float)pixels[r][c].b;
+            }
+        std::vector<int32_t> ldr(w * h * 3);
+        if (b200rt_tonemap(hdr.data(), (int64_t)(w * h), ldr.data(), 0) != B200RT_OK) {
+            std::cout << "Error: In Image::send_as_ppm(), tone mapping failed: " << b200rt_last_error() << std::endl;
+            std::exit(-1);
+        }
+        fout << "P3\n" << w << " " << h << "\n255\n";
+        for (size_t i = 0; i < w * h; ++i) fout << ldr[3 * i] << ' ' << ldr[3 * i + 1] << ' ' << ldr[3 * i + 2] << '\n';
+        std::cout << "Image successfully saved to \"" << destination << "\"" << std::endl;
+    }
+};
+
+// ===== scene flattening (the host half of the drop-in boundary) ==============================
+namespace b200rt_host {
+
+struct FlatScene {
+    std::vector<B200rtMaterial> materials;
+    std::vector<B200rtSphere> spheres;
+    std::vector<B200rtQuad> quads;
+    B200rtSceneDesc desc() const {
+        return B200rtSceneDesc{materials.size(), spheres.size(), quads.size(), materials.data(), spheres.data(), quads.data()};
+    }
+};
+
+// Canonical primitive order = get_primitive_components() order (scene.h:85-105); materials are
+// shared by pointer, as the reference's shared_ptr<Material> members are.
+inline bool flatten(const Scene &world, FlatScene &out, std::string &err) {
+    out = FlatScene{};
+    std::unordered_map<const Material *, uint32_t> ids;
+    auto mat_index = [&](const std::shared_ptr<Material> &m) -> uint32_t {
+        auto it = ids.find(m.get());
+        if (it != ids.end()) return it->second;
+        B200rtMaterial fm{};
+        fm.kind = (uint32_t)m->kind();
+        const RGB c = m->colour();
+        fm.rgb[0] = c.r; fm.rgb[1] = c.g; fm.rgb[2] = c.b;
+        fm.param = m->param();
+        out.materials.push_back(fm);
+        return ids[m.get()] = (uint32_t)out.materials.size() - 1;
+    };
+    const auto prims = world.get_primitive_components();
+    for (uint32_t i = 0; i < prims.size(); ++i) {
+        const Hittable *h = prims[i].get();
+        if (auto s = dynamic_cast<const Sphere *>(h)) {
+            B200rtSphere f{};
+            f.c[0] = s->center.x; f.c[1] = s->center.y; f.c[2] = s->center.z;
+            f.r = s->radius; f.mat = mat_index(s->material); f.prim = i;
+            out.spheres.push_back(f);
+        } else if (auto q = dynamic_cast<const Parallelogram *>(h)) {
+            B200rtQuad f{};
+            const Point3D &v = q->get_vertex(); const Vec3D &a = q->get_side1(), &b = q->get_side2();
+            f.v[0] = v.x; f.v[1] = v.y; f.v[2] = v.z;
+            f.s1[0] = a.x; f.s1[1] = a.y; f.s1[2] = a.z;
+            f.s2[0] = b.x; f.s2[1] = b.y; f.s2[2] = b.z;
+            f.mat = mat_index(q->get_material()); f.prim = i;
+            out.quads.push_back(f);
+        } else {
+            err = "unsupported Hittable subclass (the device path knows Sphere, Parallelogram, Box and Scene)";
+            return false;
+        }
+    }
+    return true;
+}
+
+}  // namespace b200rt_host
+
+// ===== base/camera.h ==========================================================================
+class Camera {
+    size_t image_w = 1280, image_h = 720;                                                       // camera.h:16
+    Ray3D camera{.origin = Point3D{0, 0, 0}, .dir = Vec3D{0, 0, -1}};                           // camera.h:29
+    std::optional<Point3D> camera_lookat;
+    Vec3D view_up_dir{0, 1, 0};
+    std::optional<double> focus_dist;
+    double defocus_angle = 0;
+    size_t samples_per_pixel = 1, max_depth = 10;                                               // camera.h:67-69
+    std::optional<double> vertical_fov{90}, horizontal_fov;                                     // camera.h:78 (sic: 90 radians)
+    RGB background{RGB::from_mag(0.5)};
+    uint64_t rng_seed = 0xB200;
+    B200rtStats last_stats{};
+    B200rtSceneInfo last_info{};
+
+public:
+    // Setter-level state -> the C ABI camera; Camera::init()'s derivation happens in b200rt_camera_init.
+    B200rtCamera to_abi() const {
+        B200rtCamera c{};
+        c.image_w = image_w; c.image_h = image_h; c.spp = samples_per_pixel; c.max_depth = max_depth;
+        const Vec3D dir = camera_lookat ? (*camera_lookat - camera.origin) : camera.dir;        // camera.h:95-97
+        c.center[0] = camera.origin.x; c.center[1] = camera.origin.y; c.center[2] = camera.origin.z;
+        c.dir[0] = dir.x; c.dir[1] = dir.y; c.dir[2] = dir.z;
+        c.up[0] = view_up_dir.x; c.up[1] = view_up_dir.y; c.up[2] = view_up_dir.z;
+        c.focus_dist = focus_dist.value_or(-1);
+        c.defocus_angle = defocus_angle;
+        c.vfov = vertical_fov.value_or(-1); c.hfov = horizontal_fov.value_or(-1);
+        c.background[0] = background.r; c.background[1] = background.g; c.background[2] = background.b;
+        if (b200rt_camera_init(&c) != B200RT_OK) {
+            std::cout << "Error: In Camera::init(), " << b200rt_last_error() << std::endl;
+            std::exit(-1);
+        }
+        return c;
+    }
+
+    // camera.h:301-303.  Builds the acceleration structure, uploads, renders on the GPU and
+    // returns the linear HDR image, all inside this call.
+    Image render(const Scene &world) {
+        b200rt_host::FlatScene flat;
+        std::string err;
+        if (!b200rt_host::flatten(world, flat, err)) {
+            std::cout << "Error: In Camera::render(), " << err << std::endl;
+            std::exit(-1);
+        }
+        const B200rtCamera cam = to_abi();
+        const B200rtSceneDesc desc = flat.desc();
+        B200rtRenderOpts opts{};
+        opts.seed = rng_seed;
+        std::vector<float> hdr(image_w * image_h * 3);
+        std::cout << "Rendering " << image_w << " x " << image_h << " image (" << flat.spheres.size() + flat.quads.size()
+                  << " primitives, " << samples_per_pixel << " spp) on the GPU..." << std::endl;
+        if (b200rt_render_scene(&desc, &cam, &opts, nullptr, hdr.data(), &last_stats, &last_info) != B200RT_OK) {
+            std::cout << "Error: In Camera::render(), " << b200rt_last_error() << std::endl;
+            std::exit(-1);
+        }
+        std::cout << "Constructed BVH in " << last_info.build_ms << "ms (created " << last_info.n_nodes << " BVHNodes total); rendered in "
+                  << last_stats.kernel_ms << "ms (" << (double)last_stats.paths / last_stats.kernel_ms / 1e3 << " Mpaths/s)\n" << std::endl;
+        Image img = Image::with_dimensions(image_w, image_h);
+        for (size_t r = 0; r < image_h; ++r)
+            for (size_t c = 0; c < image_w; ++c) {
+                const float *p = &hdr[(r * image_w + c) * 3];
+                img[r][c] = RGB::from_mag(p[0], p[1], p[2]);
+            }
+        return img;
+    }
+    const B200rtStats &stats() const { return last_stats; }
+    const B200rtSceneInfo &scene_info() const { return last_info; }
+    Camera &set_rng_seed(uint64_t s) { rng_seed = s; return *this; }   // extension: the GPU RNG key
+
+    // camera.h:308-406
+    Camera &set_camera_center(const Point3D &p) { camera.origin = p; return *this; }
+    Camera &set_camera_direction(const Vec3D &dir) { camera.dir = dir; return *this; }
+    Camera &set_camera_direction_towards(const Point3D &p) { camera.dir = p - camera.origin; camera_lookat.reset(); return *this; }
+    Camera &set_camera_lookat(const Point3D &p) { camera_lookat = p; return *this; }
+    Camera &set_focus_distance(double d) { focus_dist = d; return *this; }
+    Camera &set_defocus_angle(double degrees) { defocus_angle = degrees * std::numbers::pi / 180; return *this; }
+    Camera &turn_blur_off() { defocus_angle = 0; return *this; }
+    Camera &set_camera_up_direction(const Vec3D &dir) { view_up_dir = dir; return *this; }
+    Camera &set_image_width(size_t w) { image_w = w; return *this; }
+    Camera &set_image_height(size_t h) { image_h = h; return *this; }
+    Camera &set_image_dimensions(size_t w, size_t h) { image_w = w; image_h = h; return *this; }
+    Camera &set_image_by_width_and_aspect_ratio(size_t width, double aspect_ratio) {
+        auto height = static_cast<size_t>(std::round(static_cast<double>(width) / aspect_ratio));
+        return set_image_dimensions(width, std::max(size_t{1}, height));
+    }
+    Camera &set_image_by_height_and_aspect_ratio(size_t height, double aspect_ratio) {
+        auto width = static_cast<size_t>(std::round(static_cast<double>(height) * aspect_ratio));
+        return set_image_dimensions(std::max(size_t{1}, width), height);
+    }
+    Camera &set_samples_per_pixel(size_t s) { samples_per_pixel = s; return *this; }
+    Camera &set_max_depth(size_t d) { max_depth = d; return *this; }
+    Camera &set_vertical_fov(double degrees) { vertical_fov = degrees * std::numbers::pi / 180; horizontal_fov.reset(); return *this; }
+    Camera &set_horizontal_fov(double degrees) { horizontal_fov = degrees * std::numbers::pi / 180; vertical_fov.reset(); return *this; }
+    Camera &set_background(const RGB &c) { background = c; return *this; }
+};
