@@ -5,9 +5,9 @@
 // Parallelogram::hit_by (parallelogram.h:177-240).
 //
 // Precision design (DESIGN.md "Precision"):
-//  * Box tests run in FP32 on bounds rounded outward, with the ray origin's FP32 rounding error
-//    folded into a per-axis additive pad and a multiplicative slack on the final comparison, so
-//    a box test can only err towards "hit".  They never decide the answer, only prune.
+//  * Box tests run in FP32 on bounds rounded outward: one FMA per plane against o/d products
+//    formed in double and rounded outward, plus a multiplicative slack on the final comparison,
+//    so a box test can only err towards "hit".  They never decide the answer, only prune.
 //  * Primitive tests run in FP64, operation for operation as the reference writes them, and this
 //    translation unit is compiled with -fmad=false (the reference is built for baseline x86-64,
 //    no FMA contraction), so for the same ray the hit time is bit-identical to the reference's.
@@ -114,7 +114,9 @@ struct Trav {
     double a;                        // dot(dir, dir), hoisted out of Sphere::hit_by (sphere.h:49)
     double tmin;
     Hit best;                        // best.t doubles as the shrinking ray_times.max (bvh.h:651)
-    float fox, foy, foz, fix, fiy, fiz, eox, eoy, eoz;   // FP32 ray for box tests + per-axis pads
+    float fix, fiy, fiz;             // FP32 1/d for the box tests (0 on an axis the ray is parallel to)
+    float cnx, cny, cnz;             // o * (1/d), rounded UP   (+ pad): t_near = near_plane * inv - cn
+    float cfx, cfy, cfz;             // o * (1/d), rounded DOWN (- pad): t_far  = far_plane  * inv - cf
     float tmin32, tmax32;
     int nearx, neary, nearz;         // which float4 of a node is the near plane per axis
     int sp;
@@ -125,22 +127,30 @@ __device__ __forceinline__ bool trav_at_node(const Trav &T) { return !(T.cur & k
 __device__ __forceinline__ bool trav_at_leaf(const Trav &T) { return (T.cur & kLeafFlagD) && T.cur != kTravDone; }
 __device__ __forceinline__ bool trav_done(const Trav &T) { return T.cur == kTravDone; }
 
+__device__ __forceinline__ void trav_axis(double o, double d, float &inv, float &cn, float &cf) {
+    const float fd = (float)d;
+    float r = __frcp_rn(fd);
+    if (!(fabsf(r) <= 3.4028234e38f) || fd == 0.0f) r = 0.0f;   // parallel / out of FP32 range / NaN
+    const double p = o * (double)r;
+    const double pad = fabs(p) * 2.4e-7;                         // >= 2 ulp(FP32) of p
+    inv = r;
+    cn = r == 0.0f ? __int_as_float(0x7f800000) : __double2float_ru(p + pad);
+    cf = r == 0.0f ? __int_as_float(0xff800000) : __double2float_rd(p - pad);
+}
+
 __device__ __forceinline__ void trav_init(Trav &T, double ox, double oy, double oz, double dx, double dy, double dz,
                                           double tmin, double tmax) {
     T.ox = ox; T.oy = oy; T.oz = oz; T.dx = dx; T.dy = dy; T.dz = dz;
-    T.fox = (float)ox; T.foy = (float)oy; T.foz = (float)oz;
-    // 1/d in FP32.  A zero component gives +-inf on purpose: (plane - o) * inf is -inf / +inf when
-    // the origin is strictly inside / outside the slab and NaN when it lies exactly on the plane;
-    // fmaxf/fminf drop NaN operands, i.e. "no constraint from this axis", which is the right
-    // answer for a ray travelling inside a slab's boundary plane.  (The reference's own slab
-    // test, aabb.h:132-174, mishandles -0.0 here; ours does not depend on the sign of zero.)
-    T.fix = (float)(1.0 / dx); T.fiy = (float)(1.0 / dy); T.fiz = (float)(1.0 / dz);
-    // additive pad in t-space for the origin's rounding to FP32 (exact per ray, rounded up);
-    // exactly representable origins need none (and must not produce 0 * inf).
-    const double rx = fabs(ox - (double)T.fox), ry = fabs(oy - (double)T.foy), rz = fabs(oz - (double)T.foz);
-    T.eox = rx == 0.0 ? 0.0f : __double2float_ru(rx * (double)fabsf(T.fix) * 1.00001);
-    T.eoy = ry == 0.0 ? 0.0f : __double2float_ru(ry * (double)fabsf(T.fiy) * 1.00001);
-    T.eoz = rz == 0.0 ? 0.0f : __double2float_ru(rz * (double)fabsf(T.fiz) * 1.00001);
+    // Slab tests are  t = plane * inv - o * inv  as ONE FMA per plane.  The product o * inv is formed in
+    // double from the exact origin and rounded outward (plus a relative pad that also makes the
+    // bound strict), so the origin is never rounded to FP32 and the only relative errors left are
+    // the rounding of inv (2^-23) and of the FMA result (2^-24): covered by kBoxSlack.
+    // An axis with d == 0 (or |d| below FP32 range) gets inv = 0 and infinite constants, i.e. no
+    // constraint from that axis: conservative, and independent of the sign of zero (the
+    // reference's own slab test, aabb.h:132-174, mishandles -0.0).
+    trav_axis(ox, dx, T.fix, T.cnx, T.cfx);
+    trav_axis(oy, dy, T.fiy, T.cny, T.cfy);
+    trav_axis(oz, dz, T.fiz, T.cnz, T.cfz);
     T.nearx = T.fix < 0.0f ? 1 : 0; T.neary = T.fiy < 0.0f ? 3 : 2; T.nearz = T.fiz < 0.0f ? 5 : 4;
     T.tmin = tmin;
     T.tmin32 = __double2float_rd(tmin);
@@ -171,10 +181,10 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, ui
 #define B200RT_SLOT(c, k)                                                                                        \
     uint32_t key##k;                                                                                             \
     {                                                                                                            \
-        const float tn = fmaxf(fmaxf(__fmaf_rn(bnx.c - T.fox, T.fix, -T.eox), __fmaf_rn(bny.c - T.foy, T.fiy, -T.eoy)), \
-                               fmaxf(__fmaf_rn(bnz.c - T.foz, T.fiz, -T.eoz), T.tmin32));                         \
-        const float tf = fminf(fminf(__fmaf_rn(bfx.c - T.fox, T.fix, T.eox), __fmaf_rn(bfy.c - T.foy, T.fiy, T.eoy)),   \
-                               fminf(__fmaf_rn(bfz.c - T.foz, T.fiz, T.eoz), T.tmax32));                          \
+        const float tn = fmaxf(fmaxf(__fmaf_rn(bnx.c, T.fix, -T.cnx), __fmaf_rn(bny.c, T.fiy, -T.cny)),             \
+                               fmaxf(__fmaf_rn(bnz.c, T.fiz, -T.cnz), T.tmin32));                                 \
+        const float tf = fminf(fminf(__fmaf_rn(bfx.c, T.fix, -T.cfx), __fmaf_rn(bfy.c, T.fiy, -T.cfy)),             \
+                               fminf(__fmaf_rn(bfz.c, T.fiz, -T.cfz), T.tmax32));                                 \
         key##k = (tn <= tf * kBoxSlack) ? ((__float_as_uint(tn) & ~3u) | k) : 0xFFFFFFFFu;                        \
     }
     B200RT_SLOT(x, 0) B200RT_SLOT(y, 1) B200RT_SLOT(z, 2) B200RT_SLOT(w, 3)
