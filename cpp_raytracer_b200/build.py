@@ -65,7 +65,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-lpthread"]
+    extra = os.environ.get("B200RT_NVCC_EXTRA", "").split()   # experiment knob, e.g. -DB200RT_FULL_SORT
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-lpthread"]
     env = dict(os.environ)
     env.pop("CXX", None)   # this image exports a CXX wrapper without libgomp specs
     env.pop("CC", None)

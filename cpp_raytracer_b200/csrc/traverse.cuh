@@ -68,6 +68,11 @@ __device__ __forceinline__ bool sphere_root(double ox, double oy, double oz, dou
     // Interval::contains_exclusive (interval.h:38); `tie_ok` additionally admits root == tmax so
     // that the caller can break the tie by primitive index.
     if (!(tmin < root && (root < tmax || (tie_ok && root == tmax)))) {
+        // sphere.h:67 tries the larger root next.  With a > 0 the larger root is >= the smaller one
+        // (division by a positive number and -b -/+ sq are monotone under rounding), so once the
+        // smaller root is already past tmin it failed on the tmax side and the larger one fails too:
+        // same answer as the reference without the second division.
+        if (a > 0 && root > tmin) return false;
         root = (-b_half + sq) / a;
         if (!(tmin < root && (root < tmax || (tie_ok && root == tmax)))) return false;
     }
@@ -189,7 +194,9 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, ui
     }
     B200RT_SLOT(x, 0) B200RT_SLOT(y, 1) B200RT_SLOT(z, 2) B200RT_SLOT(w, 3)
 #undef B200RT_SLOT
-    // sort the four keys ascending (nearest first); misses sink to the end
+    // Sort the four keys ascending (nearest first); misses sink to the end.  (Pushing the three
+    // farther children UNSORTED, each with its entry distance, was measured: node visits per ray
+    // unchanged within 0.2 %, but 2-3 % slower -- four predicated pushes cost more than the network.)
     B200RT_CSWAP(key0, key1) B200RT_CSWAP(key2, key3) B200RT_CSWAP(key0, key2)
     B200RT_CSWAP(key1, key3) B200RT_CSWAP(key1, key2)
 #define B200RT_CHILD(key) ((uint32_t)(((key) & 3u) == 0 ? ch.x : ((key) & 3u) == 1 ? ch.y : ((key) & 3u) == 2 ? ch.z : ch.w))
