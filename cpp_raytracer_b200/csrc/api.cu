@@ -9,6 +9,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <string>
@@ -67,6 +68,9 @@ struct SceneImpl {
     double *d_rays = nullptr; int32_t *d_prim = nullptr; double *d_t = nullptr;   // raycast scratch
     size_t ray_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void *d_pool = nullptr;          // wavefront path-slot pool
+    uint32_t pool_slots = 0;
+    int sm_count = 148;
 };
 
 SceneImpl *as_scene(void *h) {
@@ -191,6 +195,7 @@ void free_scene(SceneImpl *s) {
     if (s->d_rays) cudaFree(s->d_rays);
     if (s->d_prim) cudaFree(s->d_prim);
     if (s->d_t) cudaFree(s->d_t);
+    if (s->d_pool) cudaFree(s->d_pool);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     s->magic = 0;
@@ -221,7 +226,8 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
     if (opts) o = *opts;
     const uint64_t count = o.sample_count ? o.sample_count : cam->spp;
     if (count > 0xFFFFFFFFull || o.sample_offset + count > 0xFFFFFFFFull) return fail(B200RT_EINVAL, "sample range out of range");
-    if (o.variant != B200RT_VARIANT_MEGAKERNEL && o.variant != B200RT_VARIANT_MEGAKERNEL_VOTED)
+    if (o.variant != B200RT_VARIANT_MEGAKERNEL && o.variant != B200RT_VARIANT_MEGAKERNEL_VOTED &&
+        o.variant != B200RT_VARIANT_WAVEFRONT)
         return fail(B200RT_EINVAL, "unknown kernel variant");
     P.scene = s->d;
     P.seed = o.seed;
@@ -232,14 +238,32 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
     P.scale = (o.flags & B200RT_FLAG_SUM) || count == 0 ? 1.0f : (float)(1.0 / (double)count);
     P.counters = s->d_counters;
     CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 3 * sizeof(unsigned long long), st));
+    unsigned long long launches = 1;
     CUDA_TRY(cudaEventRecord(s->ev0, st));
-    CUDA_TRY(launch_path_megakernel(s->stack, P, (o.flags & B200RT_FLAG_COUNTERS) != 0,
-                                    o.variant == B200RT_VARIANT_MEGAKERNEL_VOTED, st));
+    if (o.variant == B200RT_VARIANT_WAVEFRONT) {
+        // pool of path slots: 2^21 by default (B200RT_WF_SLOTS overrides, for experiments)
+        uint32_t want = 1u << 21;
+        if (const char *e = std::getenv("B200RT_WF_SLOTS")) want = (uint32_t)std::max(1024ll, std::atoll(e));
+        const unsigned long long items = (unsigned long long)cam->image_w * cam->image_h * count;
+        if (items < want) want = (uint32_t)std::max(1024ull, items);
+        if (want != s->pool_slots) {
+            if (s->d_pool) { cudaFree(s->d_pool); s->d_pool = nullptr; s->pool_slots = 0; }
+            CUDA_TRY(cudaMalloc(&s->d_pool, wavefront_pool_alloc_bytes(want)));
+            s->pool_slots = want;
+        }
+        WavefrontPool W{};
+        wavefront_pool_layout(s->d_pool, s->pool_slots, W);
+        launches = 0;
+        CUDA_TRY(run_wavefront(s->stack, P, W, (o.flags & B200RT_FLAG_COUNTERS) != 0, st, s->sm_count, &launches));
+    } else {
+        CUDA_TRY(launch_path_megakernel(s->stack, P, (o.flags & B200RT_FLAG_COUNTERS) != 0,
+                                        o.variant == B200RT_VARIANT_MEGAKERNEL_VOTED, st));
+    }
     CUDA_TRY(cudaEventRecord(s->ev1, st));
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         stats->paths = (uint64_t)cam->image_w * cam->image_h * count;
-        stats->kernel_launches = 1;
+        stats->kernel_launches = launches;
         if (sync_for_stats) {
             unsigned long long c[3];
             CUDA_TRY(cudaMemcpyAsync(c, s->d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
@@ -367,6 +391,7 @@ int b200rt_scene_create(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts
     s->d.nodes = d_nodes;
     if (!rc) {
         cudaError_t e = cudaMalloc(&s->d_counters, 3 * sizeof(unsigned long long));
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();

@@ -21,6 +21,35 @@ struct RenderParams {
     unsigned long long *counters;      // [0] rays, [1] node visits, [2] primitive tests
 };
 
+// Path-slot pool of the wavefront variant (wavefront.cu); all pointers are device memory.
+// One slot = one 128-byte line, read and written with 16-byte vector accesses.
+struct alignas(128) PathSlot {
+    double ox, oy, oz, dx, dy, dz;   //  0: the ray (direction not normalised)
+    double hit_t;                    // 48: closest hit of the last trace ...
+    uint32_t hit_ref;                // 56: ... and its primitive reference (kNoHit on a miss)
+    uint32_t pixel;                  // 60: pixel index; 0xFFFFFFFF = dead slot
+    float tr, tg, tb;                // 64: path throughput
+    uint32_t sample;                 // 76
+    uint32_t bounce;                 // 80
+    uint32_t cls;                    // 84: material class of the last hit (queue it was sorted into)
+    uint32_t pad[10];
+};
+static_assert(sizeof(PathSlot) == 128, "PathSlot must be one 128-byte line");
+
+struct WavefrontPool {
+    uint32_t n_slots;
+    unsigned long long total_items;     // image_w * image_h * samples of this call
+    PathSlot *slots;
+    uint32_t *queue;                    // 5 class queues of n_slots entries each
+    uint32_t *queue_count;              // [5]
+    uint32_t *alive;
+    unsigned long long *next_item;
+};
+size_t wavefront_pool_alloc_bytes(uint32_t n_slots);
+void wavefront_pool_layout(void *base, uint32_t n_slots, WavefrontPool &W);
+cudaError_t run_wavefront(int stack, const RenderParams &P, const WavefrontPool &W, bool count, cudaStream_t st, int sm_count,
+                          unsigned long long *launches);
+
 // `stack` = traversal stack entries the scene needs (3 x depth of the 4-wide tree); the
 // launchers pick the smallest instantiation that fits (32 / 64 / 128).
 cudaError_t launch_raycast(int stack, const DeviceScene &S, const double *rays, long long n, double tmin, double tmax,

@@ -115,3 +115,35 @@ def test_counters_flag_reports_traversal_work(golden):
         b, sb = dev.render(cam, seed=3, flags=capi.FLAG_COUNTERS)
         assert np.array_equal(a, b) and sa["rays"] == sb["rays"]
         assert sb["node_visits"] > sb["rays"] and sb["prim_tests"] > 0
+
+
+@pytest.mark.parametrize("name", ["rtow_lights", "cornell", "rtow_final", "xmas"])
+def test_wavefront_variant_computes_the_same_paths_as_the_megakernel(golden, name):
+    """Both variants key Philox by (seed, pixel, sample, bounce), so every path is the same path;
+    only the order of FP32 additions into the frame differs (atomics in the wavefront variant).
+    Also exercises pool regeneration (more work items than slots) and the drain at the end."""
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    scene = golden.scene(name)
+    cam = rt.camera_with(scene.camera, image_w=96, image_h=54, spp=48, max_depth=min(int(scene.camera["max_depth"][0]), 50))
+    with rt.DeviceSceneHandle(scene) as dev:
+        a, sa = dev.render(cam, seed=99, variant=capi.VARIANT_MEGAKERNEL, flags=capi.FLAG_SUM)
+        b, sb = dev.render(cam, seed=99, variant=capi.VARIANT_WAVEFRONT, flags=capi.FLAG_SUM)
+    assert sa["rays"] == sb["rays"], "the two variants traced a different number of rays"
+    assert sb["kernel_launches"] > 3
+    tol = 1e-4 * max(1.0, float(np.abs(a).max()))
+    assert np.allclose(a, b, rtol=2e-4, atol=tol), float(np.abs(a - b).max())
+
+
+def test_wavefront_pool_smaller_than_the_frame(golden, monkeypatch):
+    """Many more (pixel, sample) items than pool slots: slots are regenerated many times."""
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    monkeypatch.setenv("B200RT_WF_SLOTS", "4096")
+    scene = golden.scene("rtow_lights")
+    cam = rt.camera_with(scene.camera, image_w=128, image_h=72, spp=16)
+    with rt.DeviceSceneHandle(scene) as dev:
+        a, sa = dev.render(cam, seed=5, variant=capi.VARIANT_MEGAKERNEL)
+        b, sb = dev.render(cam, seed=5, variant=capi.VARIANT_WAVEFRONT)
+    assert sa["rays"] == sb["rays"]
+    assert np.allclose(a, b, rtol=2e-4, atol=1e-4 * max(1.0, float(np.abs(a).max())))
