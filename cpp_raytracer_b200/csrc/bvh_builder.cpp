@@ -67,6 +67,7 @@ struct BinNode {
     Box3 box;
     uint32_t left = 0, right = 0;    // interior
     uint32_t first = 0, count = 0;   // leaf when count > 0 (range of idx[])
+    uint32_t n_prims = 0;            // primitives below this node
     uint8_t type = 0;                // leaf primitive type
 };
 
@@ -157,6 +158,7 @@ struct Builder {
         const uint32_t n = hi - lo;
         const RangeInfo info = scan(lo, hi, pool);
         nodes[node].box = info.box;
+        nodes[node].n_prims = n;
         const bool pure = info.n_quads == 0 || info.n_quads == n;
         if (n == 1) { make_leaf(node, lo, hi, info.n_quads ? 1 : 0); return true; }
 
@@ -301,31 +303,45 @@ struct Builder {
     }
 };
 
-struct Collapser {
+// Collapses (part of) the binary tree into 4-wide nodes.  Used twice: once serially for the top
+// of the tree, where subtrees below `task_threshold` primitives are recorded as tasks instead of
+// being descended into, and once per task, in parallel, into task-local arrays that are stitched
+// into the final arrays with index offsets afterwards.
+struct Emitter {
+    struct Task { uint32_t bin_node; int32_t parent; int slot; uint32_t depth4; };
     const Builder &B;
-    BuiltBVH &out;
+    std::vector<Node4> nodes;
+    std::vector<uint32_t> sphere_order, quad_order;
     uint32_t max_depth4 = 0;
+    uint64_t n_leaves = 0;
+    std::vector<Task> *tasks = nullptr;
+    uint32_t task_threshold = 0;
+
+    explicit Emitter(const Builder &b) : B(b) {}
 
     int32_t encode_leaf(const BinNode &bn) {
-        std::vector<uint32_t> &order = bn.type ? out.quad_order : out.sphere_order;
+        std::vector<uint32_t> &order = bn.type ? quad_order : sphere_order;
         const uint32_t first = (uint32_t)order.size();
         for (uint32_t i = 0; i < bn.count; ++i) {
             uint32_t prim = B.idx[bn.first + i];
             order.push_back(bn.type ? (uint32_t)(prim - B.n_spheres) : prim);
         }
-        out.n_leaves++;
+        n_leaves++;
         return (int32_t)(kLeafFlag | (bn.type ? kQuadFlag : 0u) | (bn.count << kLeafCountShift) | first);
     }
 
-    // Emits the 4-wide node for binary interior node `b`; returns its index.
+    // Emits the 4-wide node for binary interior node `b`; returns its (local) index.
     int32_t emit(uint32_t b, uint32_t depth4) {
         max_depth4 = std::max(max_depth4, depth4);
-        const int32_t me = (int32_t)out.nodes.size();
-        out.nodes.emplace_back();
+        const int32_t me = (int32_t)nodes.size();
+        nodes.emplace_back();
         uint32_t kids[4];
         int nk = 0;
         kids[nk++] = B.nodes[b].left;
         kids[nk++] = B.nodes[b].right;
+        double scale = 0;
+        for (int a = 0; a < 3; ++a) scale = std::fmax(scale, B.nodes[b].box.hi[a] - B.nodes[b].box.lo[a]);
+        if (!(scale > 0) || !std::isfinite(scale)) scale = 1;
         // Pull up the interior child with the largest box until four slots are used.
         while (nk < 4) {
             int pick = -1;
@@ -333,10 +349,7 @@ struct Collapser {
             for (int k = 0; k < nk; ++k) {
                 const BinNode &c = B.nodes[kids[k]];
                 if (c.count) continue;
-                double scale = 0;
-                for (int a = 0; a < 3; ++a) scale = std::fmax(scale, B.nodes[b].box.hi[a] - B.nodes[b].box.lo[a]);
-                if (!(scale > 0) || !std::isfinite(scale)) scale = 1;
-                double area = half_area_scaled(c.box, scale);
+                const double area = half_area_scaled(c.box, scale);
                 if (area > best) { best = area; pick = k; }
             }
             if (pick < 0) break;
@@ -356,12 +369,74 @@ struct Collapser {
             n4.lox[k] = round_down(c.box.lo[0]); n4.hix[k] = round_up(c.box.hi[0]);
             n4.loy[k] = round_down(c.box.lo[1]); n4.hiy[k] = round_up(c.box.hi[1]);
             n4.loz[k] = round_down(c.box.lo[2]); n4.hiz[k] = round_up(c.box.hi[2]);
-            n4.child[k] = c.count ? encode_leaf(c) : emit(kids[k], depth4 + 1);
+            if (c.count) n4.child[k] = encode_leaf(c);
+            else if (tasks && c.n_prims <= task_threshold) { tasks->push_back({kids[k], me, k, depth4 + 1}); n4.child[k] = 0; }
+            else n4.child[k] = emit(kids[k], depth4 + 1);
         }
-        out.nodes[me] = n4;
+        nodes[me] = n4;
         return me;
     }
 };
+
+// Collapse + emit of the whole tree rooted at binary node 0 (an interior node) into `out`.
+void collapse_tree(const Builder &B, int threads, uint64_t n, BuiltBVH &out) {
+    Emitter top(B);
+    std::vector<Emitter::Task> tasks;
+    if (threads > 1 && n >= (1u << 16)) {
+        top.tasks = &tasks;
+        top.task_threshold = (uint32_t)std::max<uint64_t>(2048, n / ((uint64_t)threads * 16));
+    }
+    top.emit(0, 1);
+    std::vector<Emitter> parts;
+    parts.reserve(tasks.size());
+    for (size_t t = 0; t < tasks.size(); ++t) parts.emplace_back(B);
+    if (!tasks.empty()) {
+        ThreadPool pool(threads);
+        pool.parallel_for((int)tasks.size(), [&](int t) {
+            parts[t].nodes.reserve(B.nodes[tasks[t].bin_node].n_prims / 2 + 4);
+            parts[t].emit(tasks[t].bin_node, tasks[t].depth4);
+        });
+    }
+    // offsets of every part inside the final arrays
+    std::vector<uint32_t> node_off(tasks.size() + 1), sph_off(tasks.size() + 1), quad_off(tasks.size() + 1);
+    node_off[0] = (uint32_t)top.nodes.size(); sph_off[0] = (uint32_t)top.sphere_order.size(); quad_off[0] = (uint32_t)top.quad_order.size();
+    for (size_t t = 0; t < tasks.size(); ++t) {
+        node_off[t + 1] = node_off[t] + (uint32_t)parts[t].nodes.size();
+        sph_off[t + 1] = sph_off[t] + (uint32_t)parts[t].sphere_order.size();
+        quad_off[t + 1] = quad_off[t] + (uint32_t)parts[t].quad_order.size();
+    }
+    out.nodes.resize(node_off.back());
+    out.sphere_order.resize(sph_off.back());
+    out.quad_order.resize(quad_off.back());
+    std::copy(top.nodes.begin(), top.nodes.end(), out.nodes.begin());
+    std::copy(top.sphere_order.begin(), top.sphere_order.end(), out.sphere_order.begin());
+    std::copy(top.quad_order.begin(), top.quad_order.end(), out.quad_order.begin());
+    out.depth = top.max_depth4;
+    out.n_leaves = top.n_leaves;
+    for (size_t t = 0; t < tasks.size(); ++t) {
+        out.nodes[tasks[t].parent].child[tasks[t].slot] = (int32_t)node_off[t];   // part-local root is index 0
+        out.depth = std::max(out.depth, parts[t].max_depth4);
+        out.n_leaves += parts[t].n_leaves;
+    }
+    auto stitch = [&](int t) {
+        const Emitter &e = parts[t];
+        for (size_t i = 0; i < e.nodes.size(); ++i) {
+            Node4 nd = e.nodes[i];
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t c = (uint32_t)nd.child[k];
+                if (!(c & kLeafFlag)) nd.child[k] = (int32_t)(c + node_off[t]);
+                else if ((c >> kLeafCountShift) & 0xF) nd.child[k] = (int32_t)(c + ((c & kQuadFlag) ? quad_off[t] : sph_off[t]));
+            }
+            out.nodes[node_off[t] + i] = nd;
+        }
+        std::copy(e.sphere_order.begin(), e.sphere_order.end(), out.sphere_order.begin() + sph_off[t]);
+        std::copy(e.quad_order.begin(), e.quad_order.end(), out.quad_order.begin() + quad_off[t]);
+    };
+    if (!tasks.empty()) {
+        ThreadPool pool(threads);
+        pool.parallel_for((int)tasks.size(), stitch);
+    }
+}
 
 }  // namespace
 
@@ -403,23 +478,22 @@ bool build_bvh4(const std::vector<Box3> &prim_boxes, uint64_t n_spheres, uint64_
     const auto t_built = std::chrono::steady_clock::now();
     out.binary_depth = B.max_depth.load();
 
-    out.nodes.reserve(n / 2 + 16);
-    out.sphere_order.reserve(n_spheres);
-    out.quad_order.reserve(n_quads);
-    Collapser C{B, out};
     if (B.nodes[0].count) {
         // single leaf at the root: wrap it in a 4-wide root with one used slot
+        Emitter e(B);
         out.nodes.push_back(root);
         const BinNode &c = B.nodes[0];
         Node4 &r = out.nodes[0];
         r.lox[0] = round_down(c.box.lo[0]); r.hix[0] = round_up(c.box.hi[0]);
         r.loy[0] = round_down(c.box.lo[1]); r.hiy[0] = round_up(c.box.hi[1]);
         r.loz[0] = round_down(c.box.lo[2]); r.hiz[0] = round_up(c.box.hi[2]);
-        r.child[0] = C.encode_leaf(c);
+        r.child[0] = e.encode_leaf(c);
+        out.sphere_order = e.sphere_order;
+        out.quad_order = e.quad_order;
+        out.n_leaves = 1;
         out.depth = 1;
     } else {
-        C.emit(0, 1);
-        out.depth = C.max_depth4;
+        collapse_tree(B, threads, n, out);
     }
     if (out.sphere_order.size() != n_spheres || out.quad_order.size() != n_quads) { *err = "internal: leaf order size mismatch"; return false; }
     if (std::getenv("B200RT_BUILD_TIMING")) {
