@@ -64,18 +64,36 @@ __device__ __forceinline__ bool sphere_root(double ox, double oy, double oz, dou
     const double disc = b_half * b_half - a * c;
     if (disc < 0) return false;
     const double sq = sqrt(disc);
-    double root = (-b_half - sq) / a;
+    const double q1 = -b_half - sq, q2 = -b_half + sq;   // the roots are q1 / a and q2 / a (sphere.h:61,67)
+    // A double division costs ~30 instructions, and most sphere tests do not end in a hit: the ray
+    // starts ON this sphere (every scattered ray re-tests the sphere it left: q1 ~ 0 < tmin * a) or
+    // the sphere lies beyond the current closest hit.  Where the outcome of the reference's
+    // `ray_times.contains_exclusive(root)` is certain WITHOUT dividing -- q is away from tmin * a or
+    // tmax * a by more than 1e-12 relative, a margin 4 orders above the division's rounding -- skip
+    // the division; otherwise do exactly what the reference does.  Outcomes are identical.
+    bool try_first = true;
+    if (a > 0) {
+        const double lo = tmin * a, hi = tmax * a;
+        const double lo_m = fabs(lo) * 1e-12, hi_m = fabs(hi) * 1e-12;
+        if (q1 > hi + hi_m) return false;                    // smaller root > tmax, so is the larger one
+        if (q1 < lo - lo_m) {                                // smaller root < tmin: sphere.h:67 goes to the larger
+            if (q2 < lo - lo_m || q2 > hi + hi_m) return false;
+            try_first = false;
+        }
+    }
+    double root;
     // Interval::contains_exclusive (interval.h:38); `tie_ok` additionally admits root == tmax so
     // that the caller can break the tie by primitive index.
-    if (!(tmin < root && (root < tmax || (tie_ok && root == tmax)))) {
-        // sphere.h:67 tries the larger root next.  With a > 0 the larger root is >= the smaller one
-        // (division by a positive number and -b -/+ sq are monotone under rounding), so once the
-        // smaller root is already past tmin it failed on the tmax side and the larger one fails too:
-        // same answer as the reference without the second division.
+    if (try_first) {
+        root = q1 / a;
+        if (tmin < root && (root < tmax || (tie_ok && root == tmax))) { root_out = root; return true; }
+        // With a > 0 the larger root is >= the smaller one (q1 <= q2 and division by a positive
+        // number are monotone under rounding): a smaller root already past tmin failed on the tmax
+        // side, and so does the larger one.
         if (a > 0 && root > tmin) return false;
-        root = (-b_half + sq) / a;
-        if (!(tmin < root && (root < tmax || (tie_ok && root == tmax)))) return false;
     }
+    root = q2 / a;
+    if (!(tmin < root && (root < tmax || (tie_ok && root == tmax)))) return false;
     root_out = root;
     return true;
 }
