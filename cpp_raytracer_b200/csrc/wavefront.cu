@@ -22,7 +22,6 @@
 // A slot is one 128-byte line (AoS) accessed with 16-byte vectors, so the class-sorted (random)
 // slot order of the shade stage still moves whole sectors.  Traffic per ray segment: trace reads
 // 64 B and writes 32 B, sort reads 32 B, shade reads 96 B and writes 96 B: ~0.3 KB.
-#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 
@@ -289,48 +288,23 @@ static cudaError_t run_wavefront_t(const RenderParams &P, WavefrontPool W, bool 
     ++*launches;
     const int trace_blocks = sm_count * 16;
     uint32_t alive = live;
-    const bool debug = std::getenv("B200RT_WF_DEBUG") != nullptr;
-    const auto t_begin = std::chrono::steady_clock::now();
-    unsigned long long waves = 0, polls = 0;
-    double poll_ms = 0;
-    for (unsigned long long wave = 0; alive != 0; ++wave) {
-        ++waves;
-        cudaEvent_t ev[4];
-        const bool timed = debug && wave >= 8 && wave < 12;
-        if (timed) { for (auto &x : ev) cudaEventCreate(&x); cudaEventRecord(ev[0], st); }
+    unsigned long long waves = 0;
+    for (; alive != 0; ++waves) {
         wf_reset<<<1, 32, 0, st>>>(W);
-        if (timed) cudaEventRecord(ev[1], st);
         if (count) wf_trace<STACK, true><<<trace_blocks, kPathBlock, 0, st>>>(P, W);
         else wf_trace<STACK, false><<<trace_blocks, kPathBlock, 0, st>>>(P, W);
-        if (timed) cudaEventRecord(ev[2], st);
         wf_sort<<<(W.n_slots + kSortBlock - 1) / kSortBlock, kSortBlock, 0, st>>>(W);
         wf_shade<<<(W.n_slots + 127) / 128, 128, 0, st>>>(P, W);
-        if (timed) {
-            cudaEventRecord(ev[3], st);
-            cudaEventSynchronize(ev[3]);
-            float a, b, c;
-            cudaEventElapsedTime(&a, ev[0], ev[1]); cudaEventElapsedTime(&b, ev[1], ev[2]); cudaEventElapsedTime(&c, ev[2], ev[3]);
-            uint32_t qc[8];
-            cudaMemcpy(qc, W.queue_count, sizeof qc, cudaMemcpyDeviceToHost);
-            std::fprintf(stderr, "[b200rt] wave %llu: reset %.1f us, trace %.1f us, sort+shade %.1f us; queues %u %u %u %u %u alive %u\n", wave,
-                         a * 1e3, b * 1e3, c * 1e3, qc[0], qc[1], qc[2], qc[3], qc[4], qc[6]);
-            for (auto &x : ev) cudaEventDestroy(x);
-        }
         *launches += 4;
-        if ((wave & 7) == 7 || W.total_items <= W.n_slots) {
-            // poll the live-slot counter (the only host round trip; every 8 waves in steady state)
-            const auto tp = std::chrono::steady_clock::now();
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if ((waves & 7) == 7 || W.total_items <= W.n_slots) {
+            // the only host round trip: poll the live-slot counter (every 8 waves in steady state)
             if ((e = cudaMemcpyAsync(&alive, W.alive, sizeof alive, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
             if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-            poll_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tp).count();
-            ++polls;
         }
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
-    if (debug)
-        std::fprintf(stderr, "[b200rt] wavefront: %llu waves, %llu polls (%.2f ms waiting in polls), host loop %.2f ms, pool %u slots\n",
-                     waves, polls, poll_ms,
-                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), W.n_slots);
+    if (std::getenv("B200RT_WF_DEBUG"))
+        std::fprintf(stderr, "[b200rt] wavefront: %llu waves over a pool of %u slots, %llu work items\n", waves, W.n_slots, W.total_items);
     return cudaSuccess;
 }
 

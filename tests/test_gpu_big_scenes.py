@@ -100,3 +100,27 @@ def test_host_cpp_render_call_writes_reference_format_ppm(scenes_bin, golden, tm
     with rt.DeviceSceneHandle(scene) as dev:
         img, _ = dev.render(rt.camera_with(scene.camera, image_w=48, image_h=40, spp=16), seed=0xB200)
     assert np.array_equal(got, rt.tonemap(img))
+
+
+@pytest.mark.parametrize("name,w,h,spp", [("rtow_lights", 1920, 1080, 16), ("xmas", 1920, 1080, 8)])
+def test_full_resolution_frame_converges_to_live_reference(scenes_bin, ref_bridge, name, w, h, spp, tmp_path):
+    """BASELINE-size frames (C2 / C4 resolution) against two live reference renders of the same
+    size: the GPU-vs-reference RMSE sits on the reference-vs-reference noise floor."""
+    if ref_bridge is None:
+        pytest.skip("oracle/_ref/ref_bridge not built")
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import scene_io
+    scene_path = str(tmp_path / "s.scene")
+    subprocess.run([scenes_bin, name, "dump", scene_path], check=True, capture_output=True)
+    scene = scene_io.load_scene(scene_path)
+    a_hdr, b_hdr = str(tmp_path / "a.hdr"), str(tmp_path / "b.hdr")
+    _bridge(ref_bridge, [name, "--w", str(w), "--h", str(h), "--spp", str(spp), "--render-seed", "31", "render", a_hdr, "render", b_hdr])
+    with rt.DeviceSceneHandle(scene) as dev:
+        G, st = dev.render(rt.camera_with(scene.camera, image_w=w, image_h=h, spp=spp), seed=77)
+    tA, tB, tG = tone(scene_io.load_hdr(a_hdr)), tone(scene_io.load_hdr(b_hdr)), tone(G)
+    rm = lambda x, y: float(np.sqrt(np.mean((x - y) ** 2)))  # noqa: E731
+    floor, got = rm(tA, tB), max(rm(tG, tA), rm(tG, tB))
+    blk = lambda a: a[: h // 8 * 8, : w // 8 * 8].reshape(h // 8, 8, w // 8, 8, 3).mean(axis=(1, 3))  # noqa: E731
+    floor_b, got_b = rm(blk(tA), blk(tB)), max(rm(blk(tG), blk(tA)), rm(blk(tG), blk(tB)))
+    print(f"{name} {w}x{h}x{spp}: RMSE {got:.5f} vs floor {floor:.5f} ({got / floor:.3f}); 8x8 blocks {got_b:.5f} vs {floor_b:.5f} ({got_b / floor_b:.3f})")
+    assert got <= 1.10 * floor and got_b <= 1.15 * floor_b
