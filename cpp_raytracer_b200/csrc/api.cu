@@ -55,6 +55,34 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Device memory comes from the device's default stream-ordered pool with its release threshold
+// raised, so that the create / render / destroy cycle of the drop-in call (one per frame) reuses
+// memory instead of paying cudaMalloc / cudaFree (and their device-wide synchronisation) each time.
+cudaError_t dev_alloc(void **p, size_t bytes) {
+    static bool pool_ready[64] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+        }
+        pool_ready[dev] = true;
+    }
+    e = cudaMallocAsync(p, bytes ? bytes : 1, 0);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    return e;
+}
+template <typename T>
+cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc(reinterpret_cast<void **>(p), bytes); }
+void dev_free(void *p) {
+    if (p) cudaFreeAsync(p, 0);
+}
+
 struct SceneImpl {
     uint32_t magic = 0xB200577Eu;
     int device = 0;
@@ -178,7 +206,7 @@ int upload(const std::vector<T> &host, const T **dev, void **slot, uint64_t &byt
     *dev = nullptr;
     if (host.empty()) return B200RT_OK;
     void *p = nullptr;
-    CUDA_TRY(cudaMalloc(&p, host.size() * sizeof(T)));
+    CUDA_TRY(dev_alloc(&p, host.size() * sizeof(T)));
     *slot = p;
     CUDA_TRY(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
     *dev = static_cast<const T *>(p);
@@ -189,13 +217,14 @@ int upload(const std::vector<T> &host, const T **dev, void **slot, uint64_t &byt
 void free_scene(SceneImpl *s) {
     if (!s) return;
     DeviceGuard g(s->device);
-    for (void *&p : s->allocs) if (p) { cudaFree(p); p = nullptr; }
-    if (s->d_counters) cudaFree(s->d_counters);
-    if (s->d_frame) cudaFree(s->d_frame);
-    if (s->d_rays) cudaFree(s->d_rays);
-    if (s->d_prim) cudaFree(s->d_prim);
-    if (s->d_t) cudaFree(s->d_t);
-    if (s->d_pool) cudaFree(s->d_pool);
+    cudaDeviceSynchronize();   // kernels of any stream may still read the scene
+    for (void *&p : s->allocs) { dev_free(p); p = nullptr; }
+    dev_free(s->d_counters);
+    dev_free(s->d_frame);
+    dev_free(s->d_rays);
+    dev_free(s->d_prim);
+    dev_free(s->d_t);
+    dev_free(s->d_pool);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     s->magic = 0;
@@ -247,8 +276,8 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
         const unsigned long long items = (unsigned long long)cam->image_w * cam->image_h * count;
         if (items < want) want = (uint32_t)std::max(1024ull, items);
         if (want != s->pool_slots) {
-            if (s->d_pool) { cudaFree(s->d_pool); s->d_pool = nullptr; s->pool_slots = 0; }
-            CUDA_TRY(cudaMalloc(&s->d_pool, wavefront_pool_alloc_bytes(want)));
+            if (s->d_pool) { cudaStreamSynchronize(st); dev_free(s->d_pool); s->d_pool = nullptr; s->pool_slots = 0; }
+            CUDA_TRY(dev_alloc(&s->d_pool, wavefront_pool_alloc_bytes(want)));
             s->pool_slots = want;
         }
         WavefrontPool W{};
@@ -390,7 +419,7 @@ int b200rt_scene_create(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts
     if (!rc) rc = upload(mats, &s->d.materials, &s->allocs[5], bytes);
     s->d.nodes = d_nodes;
     if (!rc) {
-        cudaError_t e = cudaMalloc(&s->d_counters, 3 * sizeof(unsigned long long));
+        cudaError_t e = dev_alloc(&s->d_counters, 3 * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
@@ -429,11 +458,11 @@ int b200rt_raycast(void *scene, const double *rays, int64_t n, double tmin, doub
     if (n == 0) return B200RT_OK;
     DeviceGuard g(s->device);
     if ((size_t)n > s->ray_capacity) {
-        if (s->d_rays) { cudaFree(s->d_rays); cudaFree(s->d_prim); cudaFree(s->d_t); s->d_rays = nullptr; s->d_prim = nullptr; s->d_t = nullptr; }
+        if (s->d_rays) { dev_free(s->d_rays); dev_free(s->d_prim); dev_free(s->d_t); s->d_rays = nullptr; s->d_prim = nullptr; s->d_t = nullptr; }
         s->ray_capacity = 0;
-        CUDA_TRY(cudaMalloc(&s->d_rays, (size_t)n * 6 * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&s->d_prim, (size_t)n * sizeof(int32_t)));
-        CUDA_TRY(cudaMalloc(&s->d_t, (size_t)n * sizeof(double)));
+        CUDA_TRY(dev_alloc(&s->d_rays, (size_t)n * 6 * sizeof(double)));
+        CUDA_TRY(dev_alloc(&s->d_prim, (size_t)n * sizeof(int32_t)));
+        CUDA_TRY(dev_alloc(&s->d_t, (size_t)n * sizeof(double)));
         s->ray_capacity = (size_t)n;
     }
     CUDA_TRY(cudaMemcpy(s->d_rays, rays, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice));
@@ -460,8 +489,8 @@ int b200rt_render(void *scene, const B200rtCamera *cam, const B200rtRenderOpts *
     const double t0 = now_ms();
     const size_t floats = (size_t)cam->image_w * cam->image_h * 3;
     if (floats > s->frame_floats) {
-        if (s->d_frame) { cudaFree(s->d_frame); s->d_frame = nullptr; s->frame_floats = 0; }
-        CUDA_TRY(cudaMalloc(&s->d_frame, floats * sizeof(float)));
+        if (s->d_frame) { dev_free(s->d_frame); s->d_frame = nullptr; s->frame_floats = 0; }
+        CUDA_TRY(dev_alloc(&s->d_frame, floats * sizeof(float)));
         s->frame_floats = floats;
     }
     B200rtRenderOpts o{};
@@ -523,13 +552,14 @@ int b200rt_tonemap(const float *hdr, int64_t n_pixels, int32_t *out, int clamp) 
     if (n_pixels == 0) return B200RT_OK;
     float *d_in = nullptr;
     int32_t *d_out = nullptr;
-    CUDA_TRY(cudaMalloc(&d_in, (size_t)n_pixels * 3 * sizeof(float)));
-    cudaError_t e = cudaMalloc(&d_out, (size_t)n_pixels * 3 * sizeof(int32_t));
+    CUDA_TRY(dev_alloc(&d_in, (size_t)n_pixels * 3 * sizeof(float)));
+    cudaError_t e = dev_alloc(&d_out, (size_t)n_pixels * 3 * sizeof(int32_t));
     if (e == cudaSuccess) e = cudaMemcpy(d_in, hdr, (size_t)n_pixels * 3 * sizeof(float), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = launch_tonemap(d_in, n_pixels, d_out, clamp, 0);
     if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)n_pixels * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost);
-    cudaFree(d_in);
-    if (d_out) cudaFree(d_out);
+    cudaStreamSynchronize(0);
+    dev_free(d_in);
+    dev_free(d_out);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, std::string("tonemap: ") + cudaGetErrorString(e)); }
     return B200RT_OK;
 }
