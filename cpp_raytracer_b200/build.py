@@ -16,7 +16,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200rt.so")
-SOURCES = ["api.cu", "kernels.cu", "wavefront.cu", "bvh_builder.cpp"]
+SOURCES = ["api.cu", "kernels.cu", "wavefront.cu", "lbvh.cu", "bvh_builder.cpp"]
 HEADERS = ["bvh_builder.h", "kernels.h", "thread_pool.h", "traverse.cuh", "shade.cuh", "rng.cuh",
            os.path.join("..", "..", "include", "b200rt.h")]
 

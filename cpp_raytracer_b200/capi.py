@@ -31,6 +31,7 @@ assert MATERIAL_DTYPE.itemsize == 40 and SPHERE_DTYPE.itemsize == 40 and QUAD_DT
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_LIGHT = 0, 1, 2, 3
 VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT, VARIANT_MEGAKERNEL_VOTED = 0, 1, 2
 FLAG_SUM, FLAG_ACCUMULATE, FLAG_COUNTERS = 1, 2, 4
+BUILDER_AUTO, BUILDER_HOST_SAH, BUILDER_GPU_LBVH = 0, 1, 2
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, EINTERNAL = 0, -1, -2, -3, -4, -5
 
 
@@ -41,7 +42,7 @@ class SceneDesc(C.Structure):
 
 class BuildOpts(C.Structure):
     _fields_ = [("device", C.c_int32), ("max_leaf_prims", C.c_int32), ("sah_bins", C.c_int32),
-                ("build_threads", C.c_int32)]
+                ("build_threads", C.c_int32), ("builder", C.c_int32)]
 
 
 class SceneInfo(C.Structure):
@@ -164,7 +165,7 @@ def camera_with(cam: np.ndarray, **kw) -> np.ndarray:
 def selftest_bvh(scene: HostScene, max_leaf_prims: int = 0, sah_bins: int = 0, threads: int = 0) -> dict:
     info = SceneInfo()
     desc = scene.desc()
-    bo = BuildOpts(-1, max_leaf_prims, sah_bins, threads)
+    bo = BuildOpts(-1, max_leaf_prims, sah_bins, threads, 0)
     _check(lib().b200rt_selftest_bvh(C.byref(desc), C.byref(bo), C.byref(info)))
     return info.as_dict()
 
@@ -172,10 +173,11 @@ def selftest_bvh(scene: HostScene, max_leaf_prims: int = 0, sah_bins: int = 0, t
 class DeviceSceneHandle:
     """Owns a b200rt scene handle (device-resident scene + BVH)."""
 
-    def __init__(self, scene: HostScene, device: int = -1, max_leaf_prims: int = 0, sah_bins: int = 0, threads: int = 0):
+    def __init__(self, scene: HostScene, device: int = -1, max_leaf_prims: int = 0, sah_bins: int = 0, threads: int = 0,
+                 builder: int = BUILDER_AUTO):
         self._h = C.c_void_p()
         desc = scene.desc()
-        bo = BuildOpts(device, max_leaf_prims, sah_bins, threads)
+        bo = BuildOpts(device, max_leaf_prims, sah_bins, threads, builder)
         _check(lib().b200rt_scene_create(C.byref(desc), C.byref(bo), C.byref(self._h)))
         self.host = scene
 

@@ -22,6 +22,12 @@
 
 using namespace b200rt;
 
+namespace b200rt {
+cudaError_t build_lbvh_device(const B200rtSphere *d_sph, uint32_t n_sph, const B200rtQuad *d_quads, uint32_t n_quad,
+                              double2 *out_sph, uint2 *out_sph_meta, double2 *out_quads, uint2 *out_quad_meta,
+                              float4 **nodes_out, uint32_t *n_nodes_out, uint32_t *depth_out);
+}
+
 namespace {
 
 thread_local std::string g_last_error;
@@ -306,6 +312,141 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
     return B200RT_OK;
 }
 
+std::vector<DeviceMaterial> device_materials(const B200rtSceneDesc *desc) {
+    std::vector<DeviceMaterial> mats(desc->n_materials);
+    for (uint64_t i = 0; i < desc->n_materials; ++i) {
+        const B200rtMaterial &m = desc->materials[i];
+        DeviceMaterial dm{};
+        const double k = m.kind == B200RT_MAT_LIGHT ? m.param : 1.0;   // emit() = intensity * colour (material.h:261-263)
+        dm.r = (float)(k * m.rgb[0]); dm.g = (float)(k * m.rgb[1]); dm.b = (float)(k * m.rgb[2]);
+        dm.kind = m.kind;
+        dm.param = m.kind == B200RT_MAT_METAL ? std::fmin(m.param, 1.0) : m.param;   // Metal ctor clamps fuzz (material.h:150-151)
+        mats[i] = dm;
+    }
+    return mats;
+}
+
+// Host construction: parallel binned-SAH build + 4-wide collapse (bvh_builder.cpp), leaf-ordered SoA
+// arrays assembled on the host, then uploaded.
+int scene_build_host(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, SceneImpl *s) {
+    const double t0 = now_ms();
+    std::vector<Box3> boxes;
+    compute_boxes(desc, boxes, host_threads(opts));
+    BuiltBVH bvh;
+    const char *err = nullptr;
+    if (!build_bvh4(boxes, desc->n_spheres, desc->n_quads, build_params(opts), bvh, &err))
+        return fail(B200RT_EINVAL, std::string("BVH build failed: ") + (err ? err : "?"));
+    const int need_stack = (int)(3 * bvh.depth);
+    if (need_stack > 128) return fail(B200RT_EINTERNAL, "BVH deeper than the largest traversal stack");
+
+    // ---- leaf-ordered SoA arrays ----
+    std::vector<double2> sph(desc->n_spheres * 2);
+    std::vector<uint2> sph_meta(desc->n_spheres);
+    parallel_ranges(desc->n_spheres, host_threads(opts), [&](uint64_t lo, uint64_t hi) {
+        for (uint64_t i = lo; i < hi; ++i) {
+            const B200rtSphere &s = desc->spheres[bvh.sphere_order[i]];
+            sph[2 * i] = make_double2(s.c[0], s.c[1]);
+            sph[2 * i + 1] = make_double2(s.c[2], s.r);
+            sph_meta[i] = make_uint2(s.prim, s.mat);
+        }
+    });
+    std::vector<double2> quads(desc->n_quads * 8);
+    std::vector<uint2> quad_meta(desc->n_quads);
+    parallel_ranges(desc->n_quads, host_threads(opts), [&](uint64_t lo, uint64_t hi) {
+      for (uint64_t i = lo; i < hi; ++i) {
+        const B200rtQuad &q = desc->quads[bvh.quad_order[i]];
+        const V3 s1 = v3(q.s1), s2 = v3(q.s2);
+        const V3 n = crossv(s1, s2);                 // parallelogram.h:275-279
+        const V3 un = unitv(n);
+        const V3 w = divv(n, mag2(n));
+        const double f[16] = {un.x, un.y, un.z, q.v[0], q.v[1], q.v[2], w.x, w.y, w.z,
+                              s1.x, s1.y, s1.z, s2.x, s2.y, s2.z, 0.0};
+        for (int k = 0; k < 8; ++k) quads[8 * i + k] = make_double2(f[2 * k], f[2 * k + 1]);
+        quad_meta[i] = make_uint2(q.prim, q.mat);
+      }
+    });
+    const std::vector<DeviceMaterial> mats = device_materials(desc);
+    const double t1 = now_ms();
+
+    // ---- upload ----
+    uint64_t bytes = 0;
+    int rc = B200RT_OK;
+    const float4 *d_nodes = nullptr;
+    {
+        std::vector<float4> flat(bvh.nodes.size() * 8);
+        std::memcpy(flat.data(), bvh.nodes.data(), bvh.nodes.size() * sizeof(Node4));
+        rc = upload(flat, &d_nodes, &s->allocs[0], bytes);
+    }
+    if (!rc) rc = upload(sph, &s->d.spheres, &s->allocs[1], bytes);
+    if (!rc) rc = upload(sph_meta, &s->d.sphere_meta, &s->allocs[2], bytes);
+    if (!rc) rc = upload(quads, &s->d.quads, &s->allocs[3], bytes);
+    if (!rc) rc = upload(quad_meta, &s->d.quad_meta, &s->allocs[4], bytes);
+    if (!rc) rc = upload(mats, &s->d.materials, &s->allocs[5], bytes);
+    s->d.nodes = d_nodes;
+    if (rc) return rc;
+    const double t2 = now_ms();
+    s->stack = need_stack <= 32 ? 32 : (need_stack <= 64 ? 64 : 128);
+    s->info.n_nodes = bvh.nodes.size();
+    s->info.device_bytes = bytes;
+    s->info.tree_depth = bvh.depth;
+    s->info.build_ms = t1 - t0;
+    s->info.upload_ms = t2 - t1;
+    return B200RT_OK;
+}
+
+// GPU construction (lbvh.cu): the caller's flat arrays go to the device as they are; bounds, Morton
+// order, tree, 4-wide collapse and the leaf-ordered SoA arrays are all produced there.
+// Returns B200RT_OK, or an error; `too_deep` is set when the tree needs a stack beyond 128 entries
+// (the caller then falls back to the host SAH builder).
+int scene_build_gpu(const B200rtSceneDesc *desc, SceneImpl *s, bool *too_deep) {
+    *too_deep = false;
+    const double t0 = now_ms();
+    const uint32_t n_sph = (uint32_t)desc->n_spheres, n_quad = (uint32_t)desc->n_quads;
+    uint64_t bytes = 0;
+    B200rtSphere *raw_sph = nullptr;
+    B200rtQuad *raw_quad = nullptr;
+    auto drop_raw = [&]() { dev_free(raw_sph); dev_free(raw_quad); };
+    CUDA_TRY(dev_alloc(&raw_sph, (size_t)n_sph * sizeof(B200rtSphere)));
+    CUDA_TRY(dev_alloc(&raw_quad, (size_t)n_quad * sizeof(B200rtQuad)));
+    cudaError_t e = cudaSuccess;
+    if (n_sph) e = cudaMemcpy(raw_sph, desc->spheres, (size_t)n_sph * sizeof(B200rtSphere), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && n_quad) e = cudaMemcpy(raw_quad, desc->quads, (size_t)n_quad * sizeof(B200rtQuad), cudaMemcpyHostToDevice);
+    double2 *d_sph = nullptr, *d_quads = nullptr;
+    uint2 *d_sph_meta = nullptr, *d_quad_meta = nullptr;
+    if (e == cudaSuccess) e = dev_alloc(&d_sph, (size_t)n_sph * 2 * sizeof(double2));
+    s->allocs[1] = d_sph;
+    if (e == cudaSuccess) e = dev_alloc(&d_sph_meta, (size_t)n_sph * sizeof(uint2));
+    s->allocs[2] = d_sph_meta;
+    if (e == cudaSuccess) e = dev_alloc(&d_quads, (size_t)n_quad * 8 * sizeof(double2));
+    s->allocs[3] = d_quads;
+    if (e == cudaSuccess) e = dev_alloc(&d_quad_meta, (size_t)n_quad * sizeof(uint2));
+    s->allocs[4] = d_quad_meta;
+    float4 *d_nodes = nullptr;
+    uint32_t n_nodes = 0, depth = 0;
+    if (e == cudaSuccess)
+        e = build_lbvh_device(raw_sph, n_sph, raw_quad, n_quad, d_sph, d_sph_meta, d_quads, d_quad_meta, &d_nodes, &n_nodes, &depth);
+    s->allocs[0] = d_nodes;
+    drop_raw();
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, std::string("GPU BVH build: ") + cudaGetErrorString(e)); }
+    if (3 * depth > 128) { *too_deep = true; return B200RT_OK; }
+    const std::vector<DeviceMaterial> mats = device_materials(desc);
+    if (int rc = upload(mats, &s->d.materials, &s->allocs[5], bytes)) return rc;
+    s->d.nodes = d_nodes;
+    s->d.spheres = d_sph; s->d.sphere_meta = d_sph_meta;
+    s->d.quads = d_quads; s->d.quad_meta = d_quad_meta;
+    CUDA_TRY(cudaDeviceSynchronize());
+    bytes += (uint64_t)n_nodes * sizeof(Node4) + (uint64_t)n_sph * (2 * sizeof(double2) + sizeof(uint2)) +
+             (uint64_t)n_quad * (8 * sizeof(double2) + sizeof(uint2));
+    const int need_stack = (int)(3 * depth);
+    s->stack = need_stack <= 32 ? 32 : (need_stack <= 64 ? 64 : 128);
+    s->info.n_nodes = n_nodes;
+    s->info.device_bytes = bytes;
+    s->info.tree_depth = depth;
+    s->info.build_ms = now_ms() - t0;
+    s->info.upload_ms = 0;
+    return B200RT_OK;
+}
+
 }  // namespace
 
 // ==========================================================================================
@@ -350,94 +491,40 @@ int b200rt_scene_create(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts
     if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; } }
     if (dev >= device_count_quiet()) return fail(B200RT_EINVAL, "device ordinal out of range");
 
-    // ---- build (host) ----
-    const double t0 = now_ms();
-    std::vector<Box3> boxes;
-    compute_boxes(desc, boxes, host_threads(opts));
-    BuiltBVH bvh;
-    const char *err = nullptr;
-    if (!build_bvh4(boxes, desc->n_spheres, desc->n_quads, build_params(opts), bvh, &err))
-        return fail(B200RT_EINVAL, std::string("BVH build failed: ") + (err ? err : "?"));
-    const int need_stack = (int)(3 * bvh.depth);
-    if (need_stack > 128) return fail(B200RT_EINTERNAL, "BVH deeper than the largest traversal stack");
-
-    // ---- leaf-ordered SoA arrays ----
-    std::vector<double2> sph(desc->n_spheres * 2);
-    std::vector<uint2> sph_meta(desc->n_spheres);
-    parallel_ranges(desc->n_spheres, host_threads(opts), [&](uint64_t lo, uint64_t hi) {
-        for (uint64_t i = lo; i < hi; ++i) {
-            const B200rtSphere &s = desc->spheres[bvh.sphere_order[i]];
-            sph[2 * i] = make_double2(s.c[0], s.c[1]);
-            sph[2 * i + 1] = make_double2(s.c[2], s.r);
-            sph_meta[i] = make_uint2(s.prim, s.mat);
-        }
-    });
-    std::vector<double2> quads(desc->n_quads * 8);
-    std::vector<uint2> quad_meta(desc->n_quads);
-    parallel_ranges(desc->n_quads, host_threads(opts), [&](uint64_t lo, uint64_t hi) {
-      for (uint64_t i = lo; i < hi; ++i) {
-        const B200rtQuad &q = desc->quads[bvh.quad_order[i]];
-        const V3 s1 = v3(q.s1), s2 = v3(q.s2);
-        const V3 n = crossv(s1, s2);                 // parallelogram.h:275-279
-        const V3 un = unitv(n);
-        const V3 w = divv(n, mag2(n));
-        const double f[16] = {un.x, un.y, un.z, q.v[0], q.v[1], q.v[2], w.x, w.y, w.z,
-                              s1.x, s1.y, s1.z, s2.x, s2.y, s2.z, 0.0};
-        for (int k = 0; k < 8; ++k) quads[8 * i + k] = make_double2(f[2 * k], f[2 * k + 1]);
-        quad_meta[i] = make_uint2(q.prim, q.mat);
-      }
-    });
-    std::vector<DeviceMaterial> mats(desc->n_materials);
-    for (uint64_t i = 0; i < desc->n_materials; ++i) {
-        const B200rtMaterial &m = desc->materials[i];
-        DeviceMaterial dm{};
-        const double k = m.kind == B200RT_MAT_LIGHT ? m.param : 1.0;   // emit() = intensity * colour (material.h:261-263)
-        dm.r = (float)(k * m.rgb[0]); dm.g = (float)(k * m.rgb[1]); dm.b = (float)(k * m.rgb[2]);
-        dm.kind = m.kind;
-        dm.param = m.kind == B200RT_MAT_METAL ? std::fmin(m.param, 1.0) : m.param;   // Metal ctor clamps fuzz (material.h:150-151)
-        mats[i] = dm;
-    }
-    const double t1 = now_ms();
-
-    // ---- upload ----
     SceneImpl *s = new SceneImpl();
     s->device = dev;
     DeviceGuard g(dev);
     if (!g.ok) { delete s; return fail(B200RT_ECUDA, "cudaSetDevice failed"); }
-    uint64_t bytes = 0;
-    int rc = B200RT_OK;
-    const float4 *d_nodes = nullptr;
-    {
-        std::vector<float4> flat(bvh.nodes.size() * 8);
-        std::memcpy(flat.data(), bvh.nodes.data(), bvh.nodes.size() * sizeof(Node4));
-        rc = upload(flat, &d_nodes, &s->allocs[0], bytes);
+    const uint64_t n_prims = desc->n_spheres + desc->n_quads;
+    int builder = opts ? opts->builder : B200RT_BUILDER_AUTO;
+    // AUTO: SAH on the host for small scenes (sub-millisecond, slightly better trees: +5 % on the
+    // 4 k-sphere scene), Morton LBVH on the GPU from 64 k primitives up (2.2 M / 3.1 M primitives:
+    // 57 / 90 ms incl. the upload vs 0.8 / 1.0 s, with equal or better render rates)
+    if (builder == B200RT_BUILDER_AUTO) builder = n_prims >= 65536 ? B200RT_BUILDER_GPU_LBVH : B200RT_BUILDER_HOST_SAH;
+    bool built = false;
+    if (builder == B200RT_BUILDER_GPU_LBVH && n_prims >= 2) {
+        bool too_deep = false;
+        if (int rc = scene_build_gpu(desc, s, &too_deep)) { free_scene(s); return rc; }
+        if (too_deep) {   // pathological depth: start over with the depth-capped host builder
+            for (void *&p : s->allocs) { dev_free(p); p = nullptr; }
+        } else {
+            built = true;
+        }
     }
-    if (!rc) rc = upload(sph, &s->d.spheres, &s->allocs[1], bytes);
-    if (!rc) rc = upload(sph_meta, &s->d.sphere_meta, &s->allocs[2], bytes);
-    if (!rc) rc = upload(quads, &s->d.quads, &s->allocs[3], bytes);
-    if (!rc) rc = upload(quad_meta, &s->d.quad_meta, &s->allocs[4], bytes);
-    if (!rc) rc = upload(mats, &s->d.materials, &s->allocs[5], bytes);
-    s->d.nodes = d_nodes;
-    if (!rc) {
+    if (!built) {
+        if (int rc = scene_build_host(desc, opts, s)) { free_scene(s); return rc; }
+    }
+    {
         cudaError_t e = dev_alloc(&s->d_counters, 3 * sizeof(unsigned long long));
         if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
         if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
         if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) rc = fail(B200RT_ECUDA, std::string("scene setup: ") + cudaGetErrorString(e));
+        if (e != cudaSuccess) { free_scene(s); return fail(B200RT_ECUDA, std::string("scene setup: ") + cudaGetErrorString(e)); }
     }
-    if (rc) { free_scene(s); return rc; }
-    const double t2 = now_ms();
-
-    s->stack = need_stack <= 32 ? 32 : (need_stack <= 64 ? 64 : 128);
     s->info.n_prims = desc->n_spheres + desc->n_quads;
     s->info.n_spheres = desc->n_spheres; s->info.n_quads = desc->n_quads; s->info.n_materials = desc->n_materials;
-    s->info.n_nodes = bvh.nodes.size();
-    s->info.device_bytes = bytes;
-    s->info.tree_depth = bvh.depth;
     s->info.stack_entries = (uint32_t)s->stack;
-    s->info.build_ms = t1 - t0;
-    s->info.upload_ms = t2 - t1;
     *scene_out = s;
     return B200RT_OK;
 }

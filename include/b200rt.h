@@ -86,7 +86,15 @@ typedef struct B200rtBuildOpts {
     int32_t max_leaf_prims;  /* 1..8, 0 = default */
     int32_t sah_bins;        /* 4..64, 0 = default */
     int32_t build_threads;   /* host threads for the builder, 0 = all */
+    int32_t builder;         /* B200RT_BUILDER_* */
 } B200rtBuildOpts;
+
+enum {
+    B200RT_BUILDER_AUTO = 0,       /* HOST_SAH below 65536 primitives, GPU_LBVH from there up */
+    B200RT_BUILDER_HOST_SAH = 1,   /* parallel binned SAH on the host: best trees, ~0.3 us per primitive */
+    B200RT_BUILDER_GPU_LBVH = 2    /* Morton-order LBVH built on the GPU: tens of ms for millions of primitives,
+                                      somewhat more node visits per ray; falls back to HOST_SAH if too deep */
+};
 
 typedef struct B200rtSceneInfo {
     uint64_t n_prims, n_spheres, n_quads, n_materials;

@@ -6,7 +6,8 @@ n = int(sys.argv[1]); spp = sys.argv[2] if len(sys.argv) > 2 else "256"
 out = os.path.join(ROOT, "gpurun_out", f"scaling_{n}.jsonl")
 os.makedirs(os.path.dirname(out), exist_ok=True)
 open(out, "w").close()
-for i, wl in enumerate(["C1", "C2", "C3", "C4", "C4b", "C5"]):
+only = os.environ.get("ONLY", "C1,C2,C3,C4,C4b,C5").split(",")
+for i, wl in enumerate(only):
     cmd = ["bench.py", "--gpus", str(n), "--steps", "2", "--warmup", "3", "--workload", wl, "--spp", spp, "--no-cpu-baseline"]
     if n > 1:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
