@@ -43,7 +43,7 @@ __device__ __forceinline__ PixelMap map_pixel(const CameraParams &C) {
     const uint32_t tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
     PixelMap m;
     m.px = tile_x * 8u + (threadIdx.x & 7u);
-    m.py = tile_y * 8u + (threadIdx.x >> 3);
+    m.py = tile_y * (uint32_t)kPathTileH + (threadIdx.x >> 3);
     m.valid = m.px < C.w && m.py < C.h;
     m.pixel = m.py * C.w + m.px;
     return m;
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kPathBlock) path_megakernel_voted(const __grid
 // path_megakernel (variant 0, default): every lane runs traverse-then-shade in a loop and starts
 // its next sample as soon as a path ends.  64 registers (16 blocks = 32 warps per SM) measured
 // fastest on B200: 8/12/16/20/24 blocks per SM gave 2707/3171/3263/2630/2307 Mpaths/s on C2.
-template <int STACK, bool COUNT, int MINB = 16>
+template <int STACK, bool COUNT, int MINB = kPathMinBlocks>
 __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel(const __grid_constant__ RenderParams P) {
     const CameraParams &C = P.cam;
     const PixelMap m = map_pixel(C);
@@ -238,7 +238,7 @@ cudaError_t launch_raycast(int stack, const DeviceScene &S, const double *rays, 
 
 template <int STACK>
 static cudaError_t launch_path_t(const RenderParams &P, bool count, bool voted, cudaStream_t st) {
-    const uint32_t tiles = ((P.cam.w + 7u) >> 3) * ((P.cam.h + 7u) >> 3);
+    const uint32_t tiles = ((P.cam.w + 7u) >> 3) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
     if (tiles == 0) return cudaSuccess;
     if (!voted) {
         if (count) path_megakernel<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);

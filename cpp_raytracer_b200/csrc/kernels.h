@@ -7,7 +7,12 @@
 
 namespace b200rt {
 
-constexpr int kPathBlock = 64;
+#ifndef B200RT_PATH_BLOCK
+#define B200RT_PATH_BLOCK 64
+#endif
+constexpr int kPathBlock = B200RT_PATH_BLOCK;       // threads per block of the path kernels: an 8 x (kPathBlock/8) pixel tile
+constexpr int kPathTileH = kPathBlock / 8;
+constexpr int kPathMinBlocks = 1024 / kPathBlock;   // 1024 threads = 32 warps per SM at 64 registers
 constexpr uint32_t kRenderAccumulate = 2u;   // == B200RT_FLAG_ACCUMULATE
 
 struct RenderParams {

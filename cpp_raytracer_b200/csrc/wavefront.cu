@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) wf_generate(const __grid_constant__ Rende
 // warp's chunk -- no lane waits for the longest ray of its warp, and there is no global atomic
 // on the ray-fetch path.
 template <int STACK, bool COUNT>
-__global__ void __launch_bounds__(kPathBlock, 16) wf_trace(const __grid_constant__ RenderParams P, const WavefrontPool W) {
+__global__ void __launch_bounds__(kPathBlock, kPathMinBlocks) wf_trace(const __grid_constant__ RenderParams P, const WavefrontPool W) {
     Trav T;
     uint2 stack[STACK];
     T.cur = kTravDone;
@@ -286,7 +286,7 @@ static cudaError_t run_wavefront_t(const RenderParams &P, WavefrontPool W, bool 
     if ((e = cudaMemcpyAsync(W.alive, &live, sizeof live, cudaMemcpyHostToDevice, st)) != cudaSuccess) return e;
     wf_generate<<<(W.n_slots + 255) / 256, 256, 0, st>>>(P, W);
     ++*launches;
-    const int trace_blocks = sm_count * 16;
+    const int trace_blocks = sm_count * kPathMinBlocks;
     uint32_t alive = live;
     unsigned long long waves = 0;
     for (; alive != 0; ++waves) {
