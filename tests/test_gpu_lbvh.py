@@ -56,3 +56,27 @@ def test_lbvh_seeded_random_mixed_scene_vs_c_oracle():
     with rt.DeviceSceneHandle(scene, builder=capi.BUILDER_GPU_LBVH) as dev:
         p, t = dev.raycast(rays, 1e-5, np.inf)
     assert np.array_equal(p, want_p) and np.array_equal(t, want_t)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 33])
+def test_lbvh_tiny_and_degenerate_inputs(n):
+    """n = 1 falls back to the host builder; 2..33 primitives, all coincident (identical Morton
+    codes) or on a line, still give Scene::hit_by's answers."""
+    import os, sys
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pt_oracle
+    rng = np.random.default_rng(n)
+    for layout in ("coincident", "line"):
+        sph = np.zeros(n, capi.SPHERE_DTYPE)
+        sph["c"] = [0.0, 0.0, -5.0] if layout == "coincident" else np.stack([np.arange(n) * 2.5, np.zeros(n), np.full(n, -5.0)], axis=1)
+        sph["r"] = 1.0
+        sph["prim"] = rng.permutation(n)
+        scene = capi.HostScene(np.zeros(1, capi.MATERIAL_DTYPE), sph, np.zeros(0, capi.QUAD_DTYPE), np.zeros(1, capi.CAMERA_DTYPE))
+        rays = np.concatenate([rng.uniform(-1, 1, (256, 3)) + [0, 0, 3], rng.normal(size=(256, 3)) * [1, 0.2, 1] + [0, 0, -2]], axis=1)
+        want_p, want_t = pt_oracle.raycast_brute(scene, rays, 1e-5, np.inf)
+        with rt.DeviceSceneHandle(scene, builder=capi.BUILDER_GPU_LBVH) as dev:
+            p, t = dev.raycast(rays, 1e-5, np.inf)
+        assert np.array_equal(p, want_p) and np.array_equal(t, want_t), (n, layout)
