@@ -108,7 +108,15 @@ __device__ __forceinline__ bool quad_root(double ox, double oy, double oz, doubl
     const double den = nx * dx + ny * dy + nz * dz;
     if (fabs(den) < 1e-9) return false;
     const double ex = vx - ox, ey = vy - oy, ez = vz - oz;
-    const double t = (nx * ex + ny * ey + nz * ez) / den;
+    const double num = nx * ex + ny * ey + nz * ez;
+    {   // The plane is often hit behind the origin or beyond the current closest hit: where num / den is
+        // outside (tmin, tmax) by more than 1e-12 relative (far above the division's rounding), the
+        // reference's contains_exclusive(hit_time) is certainly false -- skip the double division.
+        const double lo = tmin * den, hi = tmax * den;
+        const double lo_m = fabs(lo) * 1e-12, hi_m = fabs(hi) * 1e-12;
+        if (den > 0 ? (num < lo - lo_m || num > hi + hi_m) : (num > lo + lo_m || num < hi - hi_m)) return false;
+    }
+    const double t = num / den;
     if (!(tmin < t && (t < tmax || (tie_ok && t == tmax)))) return false;
     const double2 q3 = __ldg(q + 3), q4 = __ldg(q + 4), q5 = __ldg(q + 5), q6 = __ldg(q + 6), q7 = __ldg(q + 7);
     const double wx = q3.x, wy = q3.y, wz = q4.x;
