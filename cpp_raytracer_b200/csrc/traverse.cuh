@@ -38,7 +38,7 @@ struct DeviceScene {
 constexpr uint32_t kLeafFlagD = 0x80000000u;
 constexpr uint32_t kQuadFlagD = 0x40000000u;
 constexpr uint32_t kNoHit = 0xFFFFFFFFu;
-constexpr float kBoxSlack = 1.0f + 1e-6f;      // covers 3 roundings (2^-24 each) on both sides
+constexpr float kBoxSlack = 1.0f + 1e-6f;      // covers inv rounding (2^-23) + FMA rounding (2^-24) on both sides: 3.6e-7
 
 struct Hit {
     double t;
@@ -54,7 +54,7 @@ __device__ __forceinline__ uint32_t canonical_prim(const DeviceScene &S, uint32_
 }
 
 // Sphere::hit_by (sphere.h:45-96).  `a` = dot(dir, dir) is hoisted out (same operations, same
-// order, so the same bits).  Returns the accepted root or a NaN-free "no" via `ok`.
+// order, so the same bits).  Returns true and the accepted root, or false.
 __device__ __forceinline__ bool sphere_root(double ox, double oy, double oz, double dx, double dy, double dz,
                                             double a, double cx, double cy, double cz, double r,
                                             double tmin, double tmax, bool tie_ok, double &root_out) {
