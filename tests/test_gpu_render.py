@@ -176,3 +176,22 @@ def test_deep_paths_cornell_depth_1000(golden):
     assert np.isfinite(a).all()
     assert sa["rays"] >= sb["rays"]
     assert abs(float(a.mean()) - float(b.mean())) < 0.05 * float(b.mean())
+
+
+@pytest.mark.parametrize("name", ["rtow_lights", "xmas", "cornell"])
+def test_tonemap_kernel_matches_c_oracle_on_reference_renders(golden, name):
+    """RGB::as_string (rgb.h:90-113) over whole reference HDR frames (lights up to 500x: values far
+    above 1, unclamped integers above 255): the tone-map kernel's integers equal the C
+    restatement's (which uses pow(v, 1/2.) exactly like the reference and is pinned by the
+    reference's own known answers) on every channel of every pixel."""
+    import os, sys
+    import cpp_raytracer_b200 as rt
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pt_oracle
+    hdr = golden.ref_image(name, "refA").astype(np.float32)
+    got = rt.tonemap(hdr)
+    want = pt_oracle.tonemap(hdr.astype(np.float64))
+    assert got.shape == want.shape
+    assert np.array_equal(got, want), f"{int((got != want).sum())} of {got.size} channels differ"
+    assert want.max() > 255 or name == "cornell"     # the no-clamp quirk is exercised
