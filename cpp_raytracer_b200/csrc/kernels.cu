@@ -113,14 +113,18 @@ __device__ __forceinline__ bool shade_and_advance(const RenderParams &P, const P
 }
 
 // ------------------------------------------------------------------------------------------
-// path_megakernel_voted (variant 2, EXPERIMENT, not the default): every lane is always in one of
-// three states (at an interior node / at a leaf / needs shading + a new ray); each iteration the
-// warp votes and executes ONLY the step kind most lanes are waiting for.  Measured on C2 it raises
-// active threads per instruction from 12.7 to 14.4 of 32 but issues 16 % more instructions
-// (the groups equilibrate near one third each), so it is no faster than the plain loop below;
-// kept so the comparison in profiles/ can be reproduced.
+// path_megakernel_voted (variant 2, EXPERIMENT, not the default).  One loop, one step per lane per
+// iteration; a lane that finished its traversal PARKS until at least B200RT_SHADE_AT lanes of the warp
+// are parked (or nobody traverses any more), then the parked lanes shade + start their next ray
+// together while the others keep traversing.  Against the default kernel this removes the tail of
+// every traversal round (where one or two slow lanes hold the warp) at the price of two ballots per
+// iteration and a shade step that runs below full width.  (An earlier form voted between node, leaf
+// and shade steps by majority: 12.7 -> 14.4 active threads per instruction, +16 % instructions, no gain.)
+#ifndef B200RT_SHADE_AT
+#define B200RT_SHADE_AT 24
+#endif
 template <int STACK, bool COUNT>
-__global__ void __launch_bounds__(kPathBlock) path_megakernel_voted(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(kPathBlock, kPathMinBlocks) path_megakernel_voted(const __grid_constant__ RenderParams P) {
     const CameraParams &C = P.cam;
     const PixelMap m = map_pixel(C);
     LaneState L;
@@ -131,31 +135,26 @@ __global__ void __launch_bounds__(kPathBlock) path_megakernel_voted(const __grid
     bool done = !(m.valid && C.max_depth > 0 && P.sample_count > 0);
 
     while (true) {
-        const bool wantN = !done && trav_at_node(T);
-        const bool wantL = !done && trav_at_leaf(T);
-        const bool wantS = !done && trav_done(T);
-        const unsigned mN = __ballot_sync(0xffffffffu, wantN);
-        const unsigned mL = __ballot_sync(0xffffffffu, wantL);
-        const unsigned mS = __ballot_sync(0xffffffffu, wantS);
-        if (!(mN | mL | mS)) break;
-        const int cN = __popc(mN), cL = __popc(mL), cS = __popc(mS);
-        if (cN >= cL && cN >= cS) {
-            if (wantN) {
-                if (COUNT) ctr.nodes++;
-                trav_node_step(P.scene, T, stack);
-            }
-        } else if (cL >= cS) {
-            if (wantL) {
-                const uint32_t c = trav_leaf_step(P.scene, T, stack);
-                if (COUNT) ctr.prims += c;
-            }
-        } else {
-            if (wantS) {
+        const bool parked = !done && trav_done(T);
+        const bool tracing = !done && !trav_done(T);
+        const unsigned m_parked = __ballot_sync(0xffffffffu, parked);
+        const unsigned m_tracing = __ballot_sync(0xffffffffu, tracing);
+        if (!(m_parked | m_tracing)) break;
+        if (m_parked && (m_tracing == 0u || __popc(m_parked) >= B200RT_SHADE_AT)) {
+            if (parked) {
                 if (shade_and_advance(P, m, T.best, L))
                     trav_init(T, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001,   // camera.h:217
                               __longlong_as_double(0x7ff0000000000000LL));
                 else
                     done = true;
+            }
+        } else if (tracing) {
+            if (trav_at_node(T)) {
+                if (COUNT) ctr.nodes++;
+                trav_node_step(P.scene, T, stack);
+            } else {
+                const uint32_t c = trav_leaf_step(P.scene, T, stack);
+                if (COUNT) ctr.prims += c;
             }
         }
     }
