@@ -63,6 +63,21 @@ int main() {
                                               std::make_shared<Metal>(RGB::random(0.5, 1), rand_double(0, 0.5))));
     world.add(std::make_shared<Box>(Point3D(2, 0, 2), Point3D(3, 1, 3), std::make_shared<DiffuseLight>(RGB::from_mag(1), 4)));
     if (world.size() != 4 || world.get_primitive_components().size() != 9) return 3;
+    // Scene container API (scene.h:19-56): add(const Scene&) copies the objects in, not the scene
+    Scene outer;
+    outer.add(world);
+    outer.add(std::make_shared<Sphere>(Point3D{9, 9, 9}, 0.5, ground));
+    if (outer.size() != 5 || outer[4] == nullptr || outer.begin() == outer.end()) return 5;
+    size_t spheres = 0;
+    for (const auto &obj : outer) if (std::dynamic_pointer_cast<Sphere>(obj)) ++spheres;
+    if (spheres != 3) return 6;
+    outer.clear();
+    if (outer.size() != 0) return 7;
+    // value-level helpers the scene functions rely on
+    if (RGB::from_rgb(255, 0, 51).r != 1.0 || RGB::from_mag(0.5).g != 0.5 || RGB::zero().b != 0.0) return 8;
+    if ((Vec3D{1, 2, 3} - Vec3D{1, 2, 3}).mag() != 0.0 || dot(Vec3D{1, 0, 0}, cross(Vec3D{0, 1, 0}, Vec3D{0, 0, 1})) != 1.0) return 9;
+    if (RGB::from_mag(10, 0.2, 0.01).as_string() != "447 63 14") return 10;          // rgb.h:90-113, the reference's own answer (kat.json)
+    if (Metal(RGB::from_mag(1), 7.0).param() != 1.0) return 11;                     // fuzz clamped to 1 (material.h:150-151)
     Camera cam;
     cam.set_image_by_width_and_aspect_ratio(64, 16. / 9.).set_vertical_fov(20).set_camera_center(Point3D{13, 2, 3})
        .set_camera_lookat(Point3D{0, 0, 0}).set_camera_up_direction(Vec3D{0, 1, 0}).set_defocus_angle(0.6)
