@@ -95,3 +95,29 @@ int main() {
     subprocess.run(["g++", "-std=c++20", "-O1", f"-I{inc}", "-o", exe, str(src), f"-L{lib}", "-lb200rt", f"-Wl,-rpath,{lib}"],
                    check=True, env=env)
     assert subprocess.run([exe], capture_output=True).returncode == 0
+
+
+def test_host_rand_double_matches_reference_stream(golden, tmp_path):
+    """rand_double / SeedSeqGenerator of the host layer vs the reference's own stream
+    (tests/golden/kat.json: set_seed(12345), then the first 16 draws of the main thread)."""
+    kat = golden.kat()
+    src = tmp_path / "lcg.cpp"
+    src.write_text('''
+#include <cstdio>
+#include "util/rand_util.h"
+int main() {
+    SeedSeqGenerator::get_instance().set_seed(%d);
+    for (int i = 0; i < 16; ++i) std::printf("%%.17g\\n", rand_double());
+    return 0;
+}
+''' % kat["rand_double_seed"])
+    exe = str(tmp_path / "lcg")
+    env = dict(os.environ)
+    env.pop("CXX", None); env.pop("CC", None)
+    inc = os.path.join(ROOT, "cpp_raytracer_b200", "host", "include")
+    lib = os.path.join(ROOT, "cpp_raytracer_b200")
+    subprocess.run(["g++", "-std=c++20", "-O1", f"-I{inc}", "-o", exe, str(src), f"-L{lib}", "-lb200rt", f"-Wl,-rpath,{lib}"],
+                   check=True, env=env)
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
+    got = [float(x) for x in out.splitlines() if x and x[0].isdigit()]
+    assert got == kat["rand_double_next16"]
