@@ -239,7 +239,8 @@ void free_scene(SceneImpl *s) {
 
 int fill_camera(const B200rtCamera *cam, CameraParams &C) {
     if (!cam) return fail(B200RT_EINVAL, "camera is NULL");
-    if (cam->image_w == 0 || cam->image_h == 0 || cam->image_w > 65536 || cam->image_h > 65536)
+    if (cam->image_w == 0 || cam->image_h == 0 || cam->image_w > 65536 || cam->image_h > 65536 ||
+        cam->image_w * cam->image_h > 0x7FFFFFFFull)   // pixel indices are 32-bit
         return fail(B200RT_EINVAL, "image dimensions out of range");
     if (cam->max_depth > 0xFFFFFFFFull) return fail(B200RT_EINVAL, "max_depth out of range");
     for (int a = 0; a < 3; ++a) {

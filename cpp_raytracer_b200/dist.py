@@ -38,7 +38,9 @@ class FrameRenderer:
     """
 
     def __init__(self, dev_scene, cam: np.ndarray, rank: int = 0, world: int = 1, device_index: int = 0,
-                 seed: int = 0xB200, variant: int = 0):
+                 seed: int = 0xB200, variant: int = 0, frame=None, ldr=None):
+        """`frame` / `ldr`: optional preallocated device tensors (H x W x 3 float32 / int32) to reuse
+        across frames instead of allocating per renderer."""
         import torch
         self.torch = torch
         self.scene = dev_scene
@@ -49,8 +51,8 @@ class FrameRenderer:
         self.spp = int(cam["spp"][0])
         self.first, self.count = sample_range(self.spp, rank, world)
         self.device = torch.device("cuda", device_index)
-        self.frame = torch.empty((self.h, self.w, 3), dtype=torch.float32, device=self.device)
-        self.ldr = torch.empty((self.h, self.w, 3), dtype=torch.int32, device=self.device)
+        self.frame = frame if frame is not None else torch.empty((self.h, self.w, 3), dtype=torch.float32, device=self.device)
+        self.ldr = ldr if ldr is not None else torch.empty((self.h, self.w, 3), dtype=torch.int32, device=self.device)
 
     def render_sum(self, want_stats: bool = False):
         from . import capi
