@@ -86,6 +86,8 @@ EXPORTS = {
     "b200rt_tonemap": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "b200rt_tonemap_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200rt_finalize_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "b200rt_finalize_peers_device": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_double, C.c_void_p,
+                                               C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200rt_selftest_bvh": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(BuildOpts), C.POINTER(SceneInfo)]),
 }
 

@@ -634,6 +634,26 @@ int b200rt_finalize_device(float *frame_device, int64_t n_pixels, double scale, 
     return B200RT_OK;
 }
 
+int b200rt_finalize_peers_device(const float *const *peer_frames, int n_peers, int rank, int64_t n_pixels, double scale,
+                                 float *root_hdr, int32_t *root_ldr_or_null, int clamp, int device, void *stream) {
+    if (n_peers < 1 || n_peers > kMaxPeers || rank < 0 || rank >= n_peers) return fail(B200RT_EINVAL, "bad peer count / rank");
+    if (n_pixels < 0 || !peer_frames || (n_pixels && !root_hdr)) return fail(B200RT_EINVAL, "bad frame buffers");
+    PeerFrames in{};
+    for (int r = 0; r < n_peers; ++r) {
+        if (n_pixels && (!peer_frames[r] || (reinterpret_cast<uintptr_t>(peer_frames[r]) & 15)))
+            return fail(B200RT_EINVAL, "peer frame pointers must be non-null and 16-byte aligned");
+        in.p[r] = peer_frames[r];
+    }
+    if ((reinterpret_cast<uintptr_t>(root_hdr) & 15) || (reinterpret_cast<uintptr_t>(root_ldr_or_null) & 15))
+        return fail(B200RT_EINVAL, "root buffers must be 16-byte aligned");
+    if (device_count_quiet() == 0) return fail(B200RT_ENODEVICE, "no CUDA device: libb200rt has no CPU path");
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; } }
+    DeviceGuard g(device);
+    CUDA_TRY(launch_reduce_finalize_peers(in, n_peers, rank, n_pixels, (float)scale, root_hdr, root_ldr_or_null, clamp,
+                                          static_cast<cudaStream_t>(stream)));
+    return B200RT_OK;
+}
+
 int b200rt_tonemap(const float *hdr, int64_t n_pixels, int32_t *out, int clamp) {
     if (n_pixels < 0 || (n_pixels && (!hdr || !out))) return fail(B200RT_EINVAL, "bad tonemap buffers");
     if (device_count_quiet() == 0) return fail(B200RT_ENODEVICE, "no CUDA device: libb200rt has no CPU path");

@@ -218,6 +218,78 @@ __global__ void finalize_kernel(float *__restrict__ frame, long long n_pixels, f
     }
 }
 
+// Multi-GPU frame exchange as ONE kernel over peer memory (NVLink / NVSwitch): this rank's slice of
+// "sum the per-rank sample sums, /= spp (camera.h:290), tone-map (rgb.h:90-113)" with the result
+// written straight into the root rank's buffers.  Every rank runs it on a different slice, so the
+// N frames cross the links once, spread over all of them (reduce-scatter + epilogue + gather in one
+// pass), instead of funnelling into rank 0.  Peers are added in rank order 0..N-1 whichever rank owns
+// the slice, so the result does not depend on the slicing.
+//   Block = kPeerTilePx pixels: coalesced float4 loads from each peer -> sum -> scale -> coalesced
+//   float4 store to the root HDR frame (may alias peer 0's buffer: each element is read and written by
+//   the same thread) -> shared memory -> per-pixel tone map -> coalesced store of the integers.
+constexpr int kPeerTilePx = 1024, kPeerThreads = 256;
+__global__ void __launch_bounds__(kPeerThreads) reduce_finalize_peers_kernel(const __grid_constant__ PeerFrames in, int n_peers, long long px_lo,
+                                                                             long long px_hi, float scale, float *root_hdr,
+                                                                             int32_t *root_ldr, int clamp) {
+    __shared__ __align__(16) float tile[kPeerTilePx * 3];
+    const long long tile_px = px_lo + (long long)blockIdx.x * kPeerTilePx;
+    const long long base = tile_px * 3;                                                     // first float of the tile
+    const long long n_fl = ((px_hi - tile_px < kPeerTilePx) ? (px_hi - tile_px) : kPeerTilePx) * 3;  // floats in this tile
+#pragma unroll
+    for (int k = 0; k < kPeerTilePx * 3 / 4 / kPeerThreads; ++k) {
+        const int j = (threadIdx.x + k * kPeerThreads) * 4;
+        if (j + 3 < n_fl) {
+            float4 a = *reinterpret_cast<const float4 *>(in.p[0] + base + j);
+            for (int r = 1; r < n_peers; ++r) {
+                const float4 b = *reinterpret_cast<const float4 *>(in.p[r] + base + j);
+                a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+            }
+            a.x *= scale; a.y *= scale; a.z *= scale; a.w *= scale;
+            *reinterpret_cast<float4 *>(root_hdr + base + j) = a;
+            *reinterpret_cast<float4 *>(tile + j) = a;
+        } else {
+            for (int e = j; e < n_fl && e < j + 4; ++e) {                                    // ragged end of the frame
+                float a = in.p[0][base + e];
+                for (int r = 1; r < n_peers; ++r) a += in.p[r][base + e];
+                a *= scale;
+                root_hdr[base + e] = a;
+                tile[e] = a;
+            }
+        }
+    }
+    if (!root_ldr) return;
+    __syncthreads();
+    int q[kPeerTilePx / kPeerThreads][3];
+#pragma unroll
+    for (int k = 0; k < kPeerTilePx / kPeerThreads; ++k) {
+        const int px = threadIdx.x + k * kPeerThreads;
+        const double r = tile[px * 3 + 0], g = tile[px * 3 + 1], b = tile[px * 3 + 2];
+        const double L = 0.2126 * r + 0.7152 * g + 0.0722 * b;
+        const double s255 = 255 + 0.999999;
+        const double v[3] = {r / (1 + L), g / (1 + L), b / (1 + L)};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            int t = (px * 3 < n_fl) ? (int)(s255 * sqrt(v[c])) : 0;
+            if (clamp) t = t < 0 ? 0 : (t > 255 ? 255 : t);
+            q[k][c] = t;
+        }
+    }
+    __syncthreads();
+    int32_t *itile = reinterpret_cast<int32_t *>(tile);
+#pragma unroll
+    for (int k = 0; k < kPeerTilePx / kPeerThreads; ++k) {
+        const int px = threadIdx.x + k * kPeerThreads;
+        itile[px * 3 + 0] = q[k][0]; itile[px * 3 + 1] = q[k][1]; itile[px * 3 + 2] = q[k][2];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kPeerTilePx * 3 / 4 / kPeerThreads; ++k) {
+        const int j = (threadIdx.x + k * kPeerThreads) * 4;
+        if (j + 3 < n_fl) *reinterpret_cast<int4 *>(root_ldr + base + j) = *reinterpret_cast<const int4 *>(itile + j);
+        else for (int e = j; e < n_fl && e < j + 4; ++e) root_ldr[base + e] = itile[e];
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 template <int STACK>
 static cudaError_t launch_raycast_t(const DeviceScene &S, const double *rays, long long n, double tmin, double tmax,
@@ -264,6 +336,24 @@ cudaError_t launch_tonemap(const float *hdr, long long n_pixels, int32_t *out, i
 cudaError_t launch_finalize(float *frame, long long n_pixels, float scale, int32_t *ldr, int clamp, cudaStream_t st) {
     if (n_pixels == 0) return cudaSuccess;
     finalize_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, st>>>(frame, n_pixels, scale, ldr, clamp);
+    return cudaGetLastError();
+}
+
+void peer_slice(long long n_pixels, int n_peers, int rank, long long *lo, long long *hi) {
+    long long chunk = (n_pixels + n_peers - 1) / n_peers;
+    chunk = (chunk + kPeerTilePx - 1) / kPeerTilePx * kPeerTilePx;        // whole tiles: slices start 16-byte aligned
+    const long long a = chunk * rank, b = a + chunk;
+    *lo = a < n_pixels ? a : n_pixels;
+    *hi = b < n_pixels ? b : n_pixels;
+}
+
+cudaError_t launch_reduce_finalize_peers(const PeerFrames &in, int n_peers, int rank, long long n_pixels, float scale,
+                                         float *root_hdr, int32_t *root_ldr, int clamp, cudaStream_t st) {
+    long long lo, hi;
+    peer_slice(n_pixels, n_peers, rank, &lo, &hi);
+    if (hi <= lo) return cudaSuccess;
+    const unsigned blocks = (unsigned)((hi - lo + kPeerTilePx - 1) / kPeerTilePx);
+    reduce_finalize_peers_kernel<<<blocks, kPeerThreads, 0, st>>>(in, n_peers, lo, hi, scale, root_hdr, root_ldr, clamp);
     return cudaGetLastError();
 }
 

@@ -63,4 +63,11 @@ cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count,
 cudaError_t launch_finalize(float *frame, long long n_pixels, float scale, int32_t *ldr, int clamp, cudaStream_t st);
 cudaError_t launch_tonemap(const float *hdr, long long n_pixels, int32_t *out, int clamp, cudaStream_t st);
 
+// Peer-memory frame exchange (multi-GPU): per-rank sum buffers addressed from this GPU.
+constexpr int kMaxPeers = 16;
+struct PeerFrames { const float *p[kMaxPeers]; };
+void peer_slice(long long n_pixels, int n_peers, int rank, long long *lo, long long *hi);
+cudaError_t launch_reduce_finalize_peers(const PeerFrames &in, int n_peers, int rank, long long n_pixels, float scale,
+                                         float *root_hdr, int32_t *root_ldr, int clamp, cudaStream_t st);
+
 }  // namespace b200rt

@@ -190,6 +190,24 @@ int b200rt_tonemap_device(const float *hdr_device, int64_t n_pixels, int32_t *ou
 int b200rt_finalize_device(float *frame_device, int64_t n_pixels, double scale, int32_t *ldr_device_or_null,
                            int clamp, int device, void *stream);
 
+/* The same epilogue with the exchange fused in, over peer-mapped memory (NVLink / NVSwitch), in place
+ * of "reduce to rank 0, then b200rt_finalize_device": one launch per rank, each rank owning one slice
+ * of the frame.  peer_frames[r] is rank r's n_pixels x 3 FP32 SUM buffer as addressable FROM THIS
+ * device (CUDA peer / symmetric-memory mapping; peer_frames[rank] is the local one); the kernel adds
+ * the n_peers buffers in rank order over its slice, scales, and writes the mean frame into root_hdr
+ * and (when given) the tone-mapped integers into root_ldr_or_null -- both pointers into the ROOT
+ * rank's memory as addressable from this device.  root_hdr may be peer_frames[0] itself (in place).
+ * All pointers must be 16-byte aligned.  The caller orders it: every rank's render must be complete
+ * and visible before any rank launches this (a device barrier across ranks), and a second barrier
+ * must pass before the root reads the result or any rank reuses its sum buffer.  Slices:
+ * chunk = ceil(n_pixels / n_peers) rounded up to 1024 pixels; rank k owns
+ * [min(n, k*chunk), min(n, (k+1)*chunk)).  1 <= n_peers <= 16.
+ * Replaces: the serial accumulation of camera.h:286-290 across GPUs (no reference counterpart for
+ * the exchange itself). */
+int b200rt_finalize_peers_device(const float *const *peer_frames, int n_peers, int rank, int64_t n_pixels,
+                                 double scale, float *root_hdr, int32_t *root_ldr_or_null, int clamp,
+                                 int device, void *stream);
+
 /* ---- host-only self test ---------------------------------------------------------------------- */
 /* Builds the acceleration structure for `desc` on the host and checks its invariants (every
  * primitive in exactly one leaf, boxes nested, reported depth exact).  Needs no GPU; fills
