@@ -31,6 +31,7 @@
 #include <random>
 #include <span>
 #include <string>
+#include <type_traits>
 #include <unordered_map>
 #include <vector>
 
@@ -232,6 +233,27 @@ public:
 };
 
 // ===== base/hittable.h, shapes/*, base/scene.h ================================================
+// base/hittable.h:20-71.  What a closest-hit query reports; the query itself runs on the GPU
+// (BVH::hit_by below), the face orientation rule is the reference's.
+struct hit_info {
+    double hit_time;
+    Point3D hit_point;
+    Vec3D unit_surface_normal;
+    bool hit_from_outside = false;
+    const Material *material;
+    hit_info(double hit_time_, const Point3D &hit_point_, const Vec3D &outward_unit_surface_normal, const Ray3D &ray,
+             const std::shared_ptr<Material> &material_)
+        : hit_time{hit_time_}, hit_point{hit_point_}, material{material_.get()} {
+        hit_from_outside = !(dot(ray.dir, outward_unit_surface_normal) > 0);                    // hittable.h:56-70
+        unit_surface_normal = hit_from_outside ? outward_unit_surface_normal : -outward_unit_surface_normal;
+    }
+};
+inline std::ostream &operator<<(std::ostream &os, const hit_info &info) {                       // hittable.h:75-80
+    os << "hit_info {\n\thit_time: " << info.hit_time << "\n\thit_point: " << info.hit_point << "\n\tsurface_normal: "
+       << info.unit_surface_normal << "\n\thit_from_outside: " << info.hit_from_outside << "\n}\n";
+    return os;
+}
+
 struct Hittable {
     // Compound objects return their parts; primitives return {} (hittable.h:112-117).
     virtual std::vector<std::shared_ptr<Hittable>> get_primitive_components() const { return {}; }
@@ -326,6 +348,11 @@ class Image {
     size_t w, h;
     std::vector<std::vector<RGB>> pixels;
     Image(size_t w_, size_t h_) : w{w_}, h{h_}, pixels(h_, std::vector<RGB>(w_, RGB::zero())) {}
+    explicit Image(const std::vector<std::vector<RGB>> &rows) : w{rows.empty() ? 0 : rows[0].size()}, h{rows.size()}, pixels{rows} {}
+    [[noreturn]] static void ppm_error(const std::string &file_name, const std::string &what) {
+        std::cout << "Error: In Image::from_ppm_file(\"" << file_name << "\"), " << what << std::endl;
+        std::exit(-1);
+    }
 public:
     auto width() const { return w; }
     auto height() const { return h; }
@@ -333,6 +360,46 @@ public:
     const auto &operator[](size_t row) const { return pixels[row]; }
     double aspect_ratio() const { return static_cast<double>(w) / static_cast<double>(h); }
     static Image with_dimensions(size_t width, size_t height) { return Image(width, height); }
+    // image.h:74-95: the missing dimension is round()ed from the aspect ratio, never below 1
+    static Image with_width_and_aspect_ratio(size_t width, double aspect_ratio) {
+        return Image(width, std::max(size_t{1}, static_cast<size_t>(std::round(static_cast<double>(width) / aspect_ratio))));
+    }
+    static Image with_height_and_aspect_ratio(size_t height, double aspect_ratio) {
+        return Image(std::max(size_t{1}, static_cast<size_t>(std::round(static_cast<double>(height) * aspect_ratio))), height);
+    }
+    static Image from_data(const std::vector<std::vector<RGB>> &img) { return Image(img); }
+    // image.h:57-66: a white one-pixel frame
+    Image &outline_border() {
+        if (w == 0 || h == 0) return *this;
+        for (auto &row : pixels) row.front() = row.back() = RGB::from_mag(1);
+        for (size_t c = 0; c < w; ++c) pixels.front()[c] = pixels.back()[c] = RGB::from_mag(1);
+        return *this;
+    }
+    // image.h:100-164: ASCII P3 only; channel values are divided by the file's own maximum.
+    static Image from_ppm_file(const std::string &file_name) {
+        std::ifstream fin(file_name);
+        if (!fin.is_open()) {
+            std::cout << "Error: In Image::from_ppm_file(), could not find/open the file \"" << file_name << "\"" << std::endl;
+            std::exit(-1);
+        }
+        std::string magic;
+        std::getline(fin, magic);
+        if (magic != "P3") ppm_error(file_name, "first line of file was not \"P3\", but instead was " + magic);
+        size_t width = 0, height = 0;
+        int max_magnitude = 0;
+        if (!(fin >> width >> height)) ppm_error(file_name, "could not parse image width and height (two integers) on second line");
+        if (!(fin >> max_magnitude)) ppm_error(file_name, "could not parse RGB max magnitude (one integer) after the image width and height");
+        Image img(width, height);
+        for (size_t i = 0; i < width * height; ++i) {
+            int r, g, b;
+            if (!(fin >> r >> g >> b)) ppm_error(file_name, "failed to parse color #" + std::to_string(i + 1) + " (three integers (r, g, b))");
+            if (r < 0 || g < 0 || b < 0)
+                ppm_error(file_name, "found negative RGB channel value; color #" + std::to_string(i + 1) + " was (" + std::to_string(r) +
+                                         ", " + std::to_string(g) + ", " + std::to_string(b) + ")");
+            img.pixels[i / width][i % width] = RGB::from_rgb(r, g, b, max_magnitude);
+        }
+        return img;
+    }
     // image.h:38-56: ASCII P3, one "r g b" line per pixel through RGB::as_string() defaults.
     // The integers come from the tone-map kernel (b200rt_tonemap), formatting stays on the host.
     void send_as_ppm(const std::string &destination) const {
@@ -356,6 +423,63 @@ public:
         fout << "P3\n" << w << " " << h << "\n255\n";
         for (size_t i = 0; i < w * h; ++i) fout << ldr[3 * i] << ' ' << ldr[3 * i + 1] << ' ' << ldr[3 * i + 2] << '\n';
         std::cout << "Image successfully saved to \"" << destination << "\"" << std::endl;
+    }
+};
+
+// image.h:168-262: a P3 writer that takes the pixels one at a time (top to bottom, left to right) and keeps
+// none of them -- the sink for progressive / tiled output.  Each pixel goes through RGB::as_string().
+class ImagePPMStream {
+    std::string file;
+    std::ofstream fout;
+    size_t w, h, written = 0;
+    ImagePPMStream(const std::string &file_, size_t w_, size_t h_) : file{file_}, fout{file_}, w{w_}, h{h_} {
+        fout << "P3\n" << w << " " << h << "\n255\n";
+    }
+public:
+    size_t width() const { return w; }
+    size_t height() const { return h; }
+    size_t size() const { return w * h; }
+    double aspect_ratio() const { return static_cast<double>(w) / static_cast<double>(h); }
+    // Redirect to another file and start the image over there (a partly written first file is reported).
+    // The reference calls open() on the still-open stream (image.h:195), which only sets failbit and
+    // silently drops every later pixel; this does what its comment describes: close, reopen, new header.
+    void set_file(const std::string &file_name) {
+        fout.close();
+        fout.clear();
+        fout.open(file_name);
+        if (!fout.is_open()) {
+            std::cout << "Error: In ImagePPMStream::set_file(), could not open the file \"" << file_name << "\"" << std::endl;
+            std::exit(-1);
+        }
+        if (written > 0)
+            std::cout << "Warning: In ImagePPMStream::set_file(\"" << file_name << "\"), original file \"" << file
+                      << "\" is left incomplete; " << written << " out of " << size() << " pixels printed" << std::endl;
+        file = file_name;
+        written = 0;
+        fout << "P3\n" << w << " " << h << "\n255\n";
+    }
+    void add(const RGB &rgb) {
+        if (written == size()) {
+            std::cout << "Error: Called ImagePPMStream::add() " << size() + 1 << " times for image of size " << size() << std::endl;
+            std::exit(-1);
+        }
+        fout << rgb.as_string() << '\n';
+        ++written;
+    }
+    static ImagePPMStream with_dimensions(size_t width, size_t height, const std::string &file_name) {
+        return ImagePPMStream(file_name, width, height);
+    }
+    static ImagePPMStream with_width_and_aspect_ratio(size_t width, double aspect_ratio, const std::string &file_name) {
+        return with_dimensions(width, std::max(size_t{1}, static_cast<size_t>(std::round(static_cast<double>(width) / aspect_ratio))), file_name);
+    }
+    static ImagePPMStream with_height_and_aspect_ratio(size_t height, double aspect_ratio, const std::string &file_name) {
+        return with_dimensions(std::max(size_t{1}, static_cast<size_t>(std::round(static_cast<double>(height) * aspect_ratio))), height, file_name);
+    }
+    ~ImagePPMStream() {
+        if (written == size()) std::cout << "Image successfully saved to \"" << file << "\"" << std::endl;
+        else
+            std::cout << "Warning: ImagePPMStream to \"" << file << "\" incomplete; " << written << " out of (" << w << " * " << h
+                      << ") = " << size() << " RGB strings printed at time of destruction" << std::endl;
     }
 };
 
@@ -413,6 +537,90 @@ inline bool flatten(const Scene &world, FlatScene &out, std::string &err) {
 
 }  // namespace b200rt_host
 
+// ===== acceleration/bvh.h =====================================================================
+// BVH(world) (bvh.h:754-776) = the scene made resident on the GPU: primitives flattened, the wide BVH built
+// (host SAH or device LBVH by size) and uploaded, ONCE; every Camera::render(bvh) / hit_by afterwards reuses
+// it.  Copies share the device scene (the reference's BVH is a value type over shared primitives).
+class BVH : public Hittable {
+    struct Resident {
+        void *handle = nullptr;
+        B200rtSceneInfo info{};
+        ~Resident() { if (handle) b200rt_scene_destroy(handle); }
+    };
+    std::shared_ptr<Resident> dev;
+    std::vector<std::shared_ptr<Hittable>> primitives;                                          // canonical order
+
+public:
+    // num_buckets / max_primitives_in_node keep their reference meaning (SAH bins per axis, leaf capacity;
+    // the device leaf format holds at most 8) and their reference defaults select the library's own.
+    template <typename T>
+        requires std::is_base_of_v<Hittable, T>
+    BVH(const T &world, size_t num_buckets = 32, size_t max_primitives_in_node = 12, int device = 0)
+        : primitives{world.get_primitive_components()} {
+        Scene flat_world;
+        if (primitives.empty()) primitives.push_back(std::shared_ptr<Hittable>(std::shared_ptr<Hittable>{}, const_cast<T *>(&world)));
+        for (const auto &p : primitives) flat_world.add(p);
+        b200rt_host::FlatScene flat;
+        std::string err;
+        if (!b200rt_host::flatten(flat_world, flat, err)) {
+            std::cout << "Error: In BVH::BVH(), " << err << std::endl;
+            std::exit(-1);
+        }
+        std::cout << "Building BVH over " << primitives.size() << " primitives..." << std::endl;
+        B200rtBuildOpts opts{};
+        opts.device = device;
+        if (num_buckets != 32) opts.sah_bins = (int32_t)num_buckets;
+        if (max_primitives_in_node != 12) opts.max_leaf_prims = (int32_t)max_primitives_in_node;
+        const B200rtSceneDesc desc = flat.desc();
+        dev = std::make_shared<Resident>();
+        if (b200rt_scene_create(&desc, &opts, &dev->handle) != B200RT_OK || b200rt_scene_info(dev->handle, &dev->info) != B200RT_OK) {
+            std::cout << "Error: In BVH::BVH(), " << b200rt_last_error() << std::endl;
+            std::exit(-1);
+        }
+        std::cout << "Constructed BVH in " << dev->info.build_ms << "ms (created " << dev->info.n_nodes << " BVHNodes total)\n" << std::endl;
+    }
+
+    void *handle() const { return dev->handle; }
+    const B200rtSceneInfo &info() const { return dev->info; }
+    auto size() const { return primitives.size(); }
+
+    // bvh.h:585-715 for a batch of rays in one launch (b200rt_raycast): closest hit with
+    // ray_times.min < t < ray_times.max per ray, exact ties to the lowest primitive index.
+    std::vector<std::optional<hit_info>> hit_by(std::span<const Ray3D> rays, const Interval &ray_times) const {
+        std::vector<double> packed(rays.size() * 6);
+        for (size_t i = 0; i < rays.size(); ++i) {
+            const Ray3D &r = rays[i];
+            double *q = &packed[i * 6];
+            q[0] = r.origin.x; q[1] = r.origin.y; q[2] = r.origin.z; q[3] = r.dir.x; q[4] = r.dir.y; q[5] = r.dir.z;
+        }
+        std::vector<int32_t> prim(rays.size());
+        std::vector<double> t(rays.size());
+        if (b200rt_raycast(dev->handle, packed.data(), (int64_t)rays.size(), ray_times.min, ray_times.max, prim.data(), t.data()) != B200RT_OK) {
+            std::cout << "Error: In BVH::hit_by(), " << b200rt_last_error() << std::endl;
+            std::exit(-1);
+        }
+        std::vector<std::optional<hit_info>> out(rays.size());
+        for (size_t i = 0; i < rays.size(); ++i) {
+            if (prim[i] < 0) continue;
+            const Hittable *h = primitives[(size_t)prim[i]].get();
+            const Point3D hit_point = rays[i](t[i]);
+            if (auto s = dynamic_cast<const Sphere *>(h))
+                out[i].emplace(t[i], hit_point, (hit_point - s->center) / s->radius, rays[i], s->material);          // sphere.h:94
+            else if (auto q = dynamic_cast<const Parallelogram *>(h))
+                out[i].emplace(t[i], hit_point, cross(q->get_side1(), q->get_side2()).unit_vector(), rays[i], q->get_material());  // parallelogram.h:225,273
+        }
+        return out;
+    }
+    std::optional<hit_info> hit_by(const Ray3D &ray, const Interval &ray_times) const {
+        return hit_by(std::span<const Ray3D>(&ray, 1), ray_times)[0];
+    }
+    std::vector<std::shared_ptr<Hittable>> get_primitive_components() const override { return primitives; }
+    void print_to(std::ostream &os) const override {
+        os << "BVH {" << dev->info.n_nodes << " 4-wide nodes, depth " << dev->info.tree_depth << ", " << primitives.size()
+           << " primitives, " << dev->info.device_bytes << " bytes on the device} " << std::flush;
+    }
+};
+
 // ===== base/camera.h ==========================================================================
 class Camera {
     size_t image_w = 1280, image_h = 720;                                                       // camera.h:16
@@ -448,6 +656,72 @@ public:
         return c;
     }
 
+    static Image to_image(const std::vector<float> &hdr, size_t w, size_t h, double scale = 1.0) {
+        Image img = Image::with_dimensions(w, h);
+        for (size_t r = 0; r < h; ++r)
+            for (size_t c = 0; c < w; ++c) {
+                const float *p = &hdr[(r * w + c) * 3];
+                img[r][c] = RGB::from_mag(p[0] * scale, p[1] * scale, p[2] * scale);
+            }
+        return img;
+    }
+
+    // camera.h:264-297 with T = BVH: renders from the scene already resident on the GPU (no build, no
+    // upload) -- the call to use for several frames / cameras over one world.
+    Image render(const BVH &bvh) {
+        const B200rtCamera cam = to_abi();
+        B200rtRenderOpts opts{};
+        opts.seed = rng_seed;
+        std::vector<float> hdr(image_w * image_h * 3);
+        if (b200rt_render(bvh.handle(), &cam, &opts, hdr.data(), &last_stats) != B200RT_OK) {
+            std::cout << "Error: In Camera::render(), " << b200rt_last_error() << std::endl;
+            std::exit(-1);
+        }
+        last_info = bvh.info();
+        return to_image(hdr, image_w, image_h);
+    }
+
+    // camera.h:264-297 for any other Hittable (a single Sphere, a Box, ...): its primitive components are
+    // rendered exactly as a Scene holding it would be.
+    template <typename T>
+        requires(std::is_base_of_v<Hittable, T> && !std::is_same_v<T, Scene> && !std::is_same_v<T, BVH>)
+    Image render(const T &world) {
+        return render(BVH(world));
+    }
+
+    // Progressive output (extension): the frame in passes of `samples_per_pass` samples over
+    // the resident scene; after each pass `on_pass(image so far, samples done)` sees the running mean.  Pass k
+    // renders samples [k*spp_pass, ...) of the same per-sample streams, so the final image is the one
+    // render(bvh) returns up to FP32 summation order.
+    template <typename F>
+    Image render_progressive(const BVH &bvh, size_t samples_per_pass, F &&on_pass) {
+        const B200rtCamera cam = to_abi();
+        std::vector<float> sum(image_w * image_h * 3, 0.0f), pass(image_w * image_h * 3);
+        B200rtStats total{};
+        size_t done = 0;
+        samples_per_pass = std::max<size_t>(1, samples_per_pass);
+        while (done < samples_per_pixel) {
+            B200rtRenderOpts opts{};
+            opts.seed = rng_seed;
+            opts.sample_offset = done;
+            opts.sample_count = std::min(samples_per_pass, samples_per_pixel - done);
+            opts.flags = B200RT_FLAG_SUM;
+            B200rtStats st{};
+            if (b200rt_render(bvh.handle(), &cam, &opts, pass.data(), &st) != B200RT_OK) {
+                std::cout << "Error: In Camera::render_progressive(), " << b200rt_last_error() << std::endl;
+                std::exit(-1);
+            }
+            for (size_t i = 0; i < sum.size(); ++i) sum[i] += pass[i];
+            done += opts.sample_count;
+            total.kernel_ms += st.kernel_ms; total.total_ms += st.total_ms; total.paths += st.paths; total.rays += st.rays;
+            total.kernel_launches += st.kernel_launches; total.d2h_bytes += st.d2h_bytes;
+            on_pass(to_image(sum, image_w, image_h, 1.0 / (double)done), done);
+        }
+        last_stats = total;
+        last_info = bvh.info();
+        return to_image(sum, image_w, image_h, 1.0 / (double)std::max<size_t>(1, done));
+    }
+
     // camera.h:301-303.  Builds the acceleration structure, uploads, renders on the GPU and
     // returns the linear HDR image, all inside this call.
     Image render(const Scene &world) {
@@ -470,13 +744,7 @@ public:
         }
         std::cout << "Constructed BVH in " << last_info.build_ms << "ms (created " << last_info.n_nodes << " BVHNodes total); rendered in "
                   << last_stats.kernel_ms << "ms (" << (double)last_stats.paths / last_stats.kernel_ms / 1e3 << " Mpaths/s)\n" << std::endl;
-        Image img = Image::with_dimensions(image_w, image_h);
-        for (size_t r = 0; r < image_h; ++r)
-            for (size_t c = 0; c < image_w; ++c) {
-                const float *p = &hdr[(r * image_w + c) * 3];
-                img[r][c] = RGB::from_mag(p[0], p[1], p[2]);
-            }
-        return img;
+        return to_image(hdr, image_w, image_h);
     }
     const B200rtStats &stats() const { return last_stats; }
     const B200rtSceneInfo &scene_info() const { return last_info; }

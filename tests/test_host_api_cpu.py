@@ -121,3 +121,66 @@ int main() {
     out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout
     got = [float(x) for x in out.splitlines() if x and x[0].isdigit()]
     assert got == kat["rand_double_next16"]
+
+
+def _compile(tmp_path, name, text):
+    src = tmp_path / f"{name}.cpp"
+    src.write_text(text)
+    exe = str(tmp_path / name)
+    env = dict(os.environ)
+    env.pop("CXX", None); env.pop("CC", None)
+    inc = os.path.join(ROOT, "cpp_raytracer_b200", "host", "include")
+    lib = os.path.join(ROOT, "cpp_raytracer_b200")
+    subprocess.run(["g++", "-std=c++20", "-O1", f"-I{inc}", "-o", exe, str(src), f"-L{lib}", "-lb200rt", f"-Wl,-rpath,{lib}"],
+                   check=True, env=env)
+    return exe
+
+
+def test_image_io_surface(tmp_path):
+    """image.h: named constructors, outline_border, the streaming P3 writer (ImagePPMStream) and the P3
+    reader (Image::from_ppm_file).  Host-only I/O: no device involved."""
+    out1, out2, inp = tmp_path / "a.ppm", tmp_path / "b.ppm", tmp_path / "in.ppm"
+    inp.write_text("P3\n2 2\n100\n50 0 100\n0 25 0\n1 2 3\n100 100 100\n")
+    exe = _compile(tmp_path, "imgio", r'''
+#include <cstdio>
+#include "util/image.h"
+int main(int argc, char **argv) {
+    if (Image::with_width_and_aspect_ratio(64, 16. / 9.).height() != 36) return 1;
+    if (Image::with_height_and_aspect_ratio(36, 16. / 9.).width() != 64) return 2;
+    if (Image::with_width_and_aspect_ratio(1, 100.).height() != 1) return 3;
+    auto img = Image::with_dimensions(4, 3);
+    img.outline_border();
+    if (img[0][2].r != 1 || img[1][0].g != 1 || img[1][3].b != 1 || img[2][1].r != 1 || img[1][1].r != 0 || img[1][2].r != 0) return 4;
+    auto data = Image::from_data({{RGB::from_mag(1), RGB::from_mag(0.25)}});
+    if (data.width() != 2 || data.height() != 1 || data[0][1].g != 0.25) return 5;
+    {
+        auto s = ImagePPMStream::with_dimensions(3, 2, argv[1]);
+        if (s.size() != 6 || s.aspect_ratio() != 1.5) return 6;
+        s.add(RGB::from_mag(10, 0.2, 0.01));                 // "447 63 14": the reference's own answer (kat.json)
+        s.add(RGB::zero());
+        s.set_file(argv[2]);                                 // restart in a second file
+        for (int i = 0; i < 6; ++i) s.add(RGB::from_mag(i == 5 ? 10 : 0, i == 5 ? 0.2 : 0, i == 5 ? 0.01 : 0));
+    }
+    auto in = Image::from_ppm_file(argv[3]);
+    if (in.width() != 2 || in.height() != 2) return 7;
+    if (in[0][0].r != 0.5 || in[0][0].g != 0 || in[0][0].b != 1 || in[0][1].g != 0.25 || in[1][0].b != 0.03 || in[1][1].r != 1) return 8;
+    return 0;
+}
+''')
+    r = subprocess.run([exe, str(out1), str(out2), str(inp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert out1.read_text() == "P3\n3 2\n255\n447 63 14\n0 0 0\n"
+    assert out2.read_text() == "P3\n3 2\n255\n" + "0 0 0\n" * 5 + "447 63 14\n"      # set_file starts the image over
+    assert "left incomplete; 2 out of 6" in r.stdout and "Image successfully saved" in r.stdout
+    bad = tmp_path / "bad.ppm"
+    bad.write_text("P6\n1 1\n255\n")
+    exe2 = _compile(tmp_path, "imgbad", '#include "util/image.h"\nint main(int, char **argv) { Image::from_ppm_file(argv[1]); return 0; }\n')
+    r = subprocess.run([exe2, str(bad)], capture_output=True, text=True)
+    assert r.returncode != 0 and 'was not "P3"' in r.stdout
+
+
+def test_bvh_reuse_program_compiles(tmp_path):
+    """The program of tests/test_gpu_host_api.py (BVH reuse, hit_by, progressive render, render<T>) builds
+    here without a GPU; it runs in the -m gpu suite."""
+    from test_gpu_host_api import PROGRAM
+    assert os.path.exists(_compile(tmp_path, "bvhprog", PROGRAM))
