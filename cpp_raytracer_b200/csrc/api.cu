@@ -385,6 +385,8 @@ int scene_build_host(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, S
     if (!rc) rc = upload(mats, &s->d.materials, &s->allocs[5], bytes);
     s->d.nodes = d_nodes;
     if (rc) return rc;
+    if (reinterpret_cast<uintptr_t>(d_nodes) & 127)   // trav_node_step forms plane addresses with OR / XOR on the low bits
+        return fail(B200RT_ECUDA, "node array is not 128-byte aligned");
     const double t2 = now_ms();
     s->stack = need_stack <= 32 ? 32 : (need_stack <= 64 ? 64 : 128);
     s->info.n_nodes = bvh.nodes.size();
@@ -432,6 +434,8 @@ int scene_build_gpu(const B200rtSceneDesc *desc, SceneImpl *s, bool *too_deep) {
     if (3 * depth > 128) { *too_deep = true; return B200RT_OK; }
     const std::vector<DeviceMaterial> mats = device_materials(desc);
     if (int rc = upload(mats, &s->d.materials, &s->allocs[5], bytes)) return rc;
+    if (reinterpret_cast<uintptr_t>(d_nodes) & 127)   // trav_node_step forms plane addresses with OR / XOR on the low bits
+        return fail(B200RT_ECUDA, "node array is not 128-byte aligned");
     s->d.nodes = d_nodes;
     s->d.spheres = d_sph; s->d.sphere_meta = d_sph_meta;
     s->d.quads = d_quads; s->d.quad_meta = d_quad_meta;

@@ -158,6 +158,21 @@ __device__ __forceinline__ bool trav_at_node(const Trav &T) { return !(T.cur & k
 __device__ __forceinline__ bool trav_at_leaf(const Trav &T) { return (T.cur & kLeafFlagD) && T.cur != kTravDone; }
 __device__ __forceinline__ bool trav_done(const Trav &T) { return T.cur == kTravDone; }
 
+// double -> float rounded towards -inf / +inf, written with plain casts and integer steps so that it
+// constant-folds when the argument is a literal (the path kernel's tmin = 0.00001, tmax = inf): the
+// cvt.rd / cvt.ru intrinsics do not fold, and under the 64-register cap the compiler then re-executes the
+// conversion (an XU-pipe instruction) in every node step instead of keeping the value in a register.
+__device__ __forceinline__ float float_toward(double x, bool up) {
+    float f = (float)x;
+    if (up ? ((double)f < x) : ((double)f > x)) {
+        int b = __float_as_int(f);
+        if (f == 0.0f) b = up ? 0x00000001 : (int)0x80000001;
+        else b += ((f > 0.0f) == up) ? 1 : -1;
+        f = __int_as_float(b);
+    }
+    return f;
+}
+
 __device__ __forceinline__ void trav_axis(double o, double d, float &inv, float &cn, float &cf) {
     const float fd = (float)d;
     float r = __frcp_rn(fd);
@@ -184,8 +199,8 @@ __device__ __forceinline__ void trav_init(Trav &T, double ox, double oy, double 
     trav_axis(oz, dz, T.fiz, T.cnz, T.cfz);
     T.nearx = T.fix < 0.0f ? 1 : 0; T.neary = T.fiy < 0.0f ? 3 : 2; T.nearz = T.fiz < 0.0f ? 5 : 4;
     T.tmin = tmin;
-    T.tmin32 = __double2float_rd(tmin);
-    T.tmax32 = __double2float_ru(tmax);
+    T.tmin32 = float_toward(tmin, false);
+    T.tmax32 = float_toward(tmax, true);
     T.a = dx * dx + dy * dy + dz * dz;
     T.best.t = tmax;
     T.best.ref = kNoHit;
@@ -202,13 +217,30 @@ __device__ __forceinline__ void trav_pop(Trav &T, const uint2 *stack) {
     }
 }
 
+// child[key & 3] without branches (the compiler's version of the ?: chain branches, and lanes of a warp
+// then serialise over up to four sub-paths per pushed entry).
+__device__ __forceinline__ uint32_t pick_child(const int4 &ch, uint32_t key) {
+    uint32_t r;
+    asm("{\n\t.reg .pred p0, p1;\n\t.reg .b32 lo, hi, b;\n\t"
+        "and.b32 b, %5, 1;\n\tsetp.ne.u32 p0, b, 0;\n\t"
+        "and.b32 b, %5, 2;\n\tsetp.ne.u32 p1, b, 0;\n\t"
+        "selp.b32 lo, %2, %1, p0;\n\tselp.b32 hi, %4, %3, p0;\n\tselp.b32 %0, hi, lo, p1;\n\t}"
+        : "=r"(r) : "r"(ch.x), "r"(ch.y), "r"(ch.z), "r"(ch.w), "r"(key));
+    return r;
+}
+
 // One interior node: conservative FP32 slab tests of its four child boxes, nearest-first order.
 __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, uint2 *stack) {
-    const float4 *n = S.nodes + (size_t)T.cur * 8;
-    const float4 bnx = __ldg(n + T.nearx), bfx = __ldg(n + (T.nearx ^ 1));
-    const float4 bny = __ldg(n + T.neary), bfy = __ldg(n + (T.neary ^ 1));
-    const float4 bnz = __ldg(n + T.nearz), bfz = __ldg(n + (T.nearz ^ 1));
-    const int4 ch = __ldg((const int4 *)(n + 6));
+    // Nodes are 128-byte aligned (checked at scene creation), so the six plane addresses are formed without
+    // carries: near = base | (0/16, 32/48, 64/80), far = near ^ 16 -- one logic op each on the low word.
+    const uintptr_t base = reinterpret_cast<uintptr_t>(S.nodes) + ((uintptr_t)T.cur << 7);
+    const uintptr_t pnx = base | (uint32_t)(T.nearx << 4), pny = base | (uint32_t)(T.neary << 4), pnz = base | (uint32_t)(T.nearz << 4);
+#define B200RT_NODE_F4(a) __ldg(reinterpret_cast<const float4 *>(a))
+    const float4 bnx = B200RT_NODE_F4(pnx), bfx = B200RT_NODE_F4(pnx ^ 16);
+    const float4 bny = B200RT_NODE_F4(pny), bfy = B200RT_NODE_F4(pny ^ 16);
+    const float4 bnz = B200RT_NODE_F4(pnz), bfz = B200RT_NODE_F4(pnz ^ 16);
+    const int4 ch = __ldg(reinterpret_cast<const int4 *>(base + 96));
+#undef B200RT_NODE_F4
 #define B200RT_SLOT(c, k)                                                                                        \
     uint32_t key##k;                                                                                             \
     {                                                                                                            \
@@ -225,7 +257,7 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, ui
     // unchanged within 0.2 %, but 2-3 % slower -- four predicated pushes cost more than the network.)
     B200RT_CSWAP(key0, key1) B200RT_CSWAP(key2, key3) B200RT_CSWAP(key0, key2)
     B200RT_CSWAP(key1, key3) B200RT_CSWAP(key1, key2)
-#define B200RT_CHILD(key) ((uint32_t)(((key) & 3u) == 0 ? ch.x : ((key) & 3u) == 1 ? ch.y : ((key) & 3u) == 2 ? ch.z : ch.w))
+#define B200RT_CHILD(key) pick_child(ch, key)
     if (key0 != 0xFFFFFFFFu) {
         if (key3 != 0xFFFFFFFFu) stack[T.sp++] = make_uint2(B200RT_CHILD(key3), key3);
         if (key2 != 0xFFFFFFFFu) stack[T.sp++] = make_uint2(B200RT_CHILD(key2), key2);
