@@ -70,6 +70,10 @@ class Stats(C.Structure):
 
 
 # every symbol include/b200rt.h declares; tests check the library exports exactly these
+SHADE_RECORD_DTYPE = np.dtype([("scattered", "<f8", 6), ("t", "<f8"), ("atten", "<f4", 3), ("emit", "<f4", 3),
+                               ("prim", "<i4"), ("flags", "<i4")])
+assert SHADE_RECORD_DTYPE.itemsize == 88
+
 EXPORTS = {
     "b200rt_device_count": (C.c_int, []),
     "b200rt_last_error": (C.c_char_p, []),
@@ -85,6 +89,7 @@ EXPORTS = {
                                       C.c_void_p, C.POINTER(Stats), C.POINTER(SceneInfo)]),
     "b200rt_tonemap": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "b200rt_tonemap_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "b200rt_debug_shade": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
     "b200rt_finalize_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200rt_finalize_peers_device": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_double, C.c_void_p,
                                                C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -212,6 +217,17 @@ class DeviceSceneHandle:
         t = np.empty(n, dtype=np.float64)
         _check(lib().b200rt_raycast(self._h, rays.ctypes.data, n, tmin, tmax, prim.ctypes.data, t.ctypes.data))
         return prim, t
+
+    def debug_shade(self, rays: np.ndarray, rnd: np.ndarray, tmin: float = 1e-5, tmax: float = float("inf")) -> np.ndarray:
+        """One surface interaction per ray with caller-supplied random words (b200rt_debug_shade);
+        returns a record array of SHADE_RECORD_DTYPE."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 6)
+        rnd = np.ascontiguousarray(rnd, dtype=np.uint32).reshape(-1, 4)
+        if rnd.shape[0] != rays.shape[0]:
+            raise ValueError("one row of four random words per ray")
+        out = np.zeros(rays.shape[0], dtype=SHADE_RECORD_DTYPE)
+        _check(lib().b200rt_debug_shade(self._h, rays.ctypes.data, rnd.ctypes.data, rays.shape[0], tmin, tmax, out.ctypes.data))
+        return out
 
     def render(self, cam: np.ndarray, seed: int = 0xB200, sample_offset: int = 0, sample_count: int = 0,
                variant: int = VARIANT_MEGAKERNEL, flags: int = 0):

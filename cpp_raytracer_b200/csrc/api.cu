@@ -564,6 +564,30 @@ int b200rt_raycast(void *scene, const double *rays, int64_t n, double tmin, doub
     return B200RT_OK;
 }
 
+int b200rt_debug_shade(void *scene, const double *rays, const uint32_t *rnd, int64_t n, double tmin, double tmax,
+                       B200rtShadeRecord *records_out) {
+    static_assert(sizeof(B200rtShadeRecord) == 88, "record layout is shared with kernels.cu");
+    SceneImpl *s = as_scene(scene);
+    if (!s) return fail(B200RT_EINVAL, "bad scene handle");
+    if (n < 0 || (n && (!rays || !rnd || !records_out))) return fail(B200RT_EINVAL, "bad debug_shade buffers");
+    if (n == 0) return B200RT_OK;
+    DeviceGuard g(s->device);
+    double *d_rays = nullptr;
+    uint32_t *d_rnd = nullptr;
+    void *d_rec = nullptr;
+    cudaError_t e = dev_alloc(&d_rays, (size_t)n * 6 * sizeof(double));
+    if (e == cudaSuccess) e = dev_alloc(&d_rnd, (size_t)n * 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = dev_alloc(&d_rec, (size_t)n * sizeof(B200rtShadeRecord));
+    if (e == cudaSuccess) e = cudaMemcpy(d_rays, rays, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_rnd, rnd, (size_t)n * 4 * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_debug_shade(s->stack, s->d, d_rays, d_rnd, n, tmin, tmax, d_rec, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(records_out, d_rec, (size_t)n * sizeof(B200rtShadeRecord), cudaMemcpyDeviceToHost);
+    cudaStreamSynchronize(0);
+    dev_free(d_rays); dev_free(d_rnd); dev_free(d_rec);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, std::string("debug_shade: ") + cudaGetErrorString(e)); }
+    return B200RT_OK;
+}
+
 int b200rt_render_device(void *scene, const B200rtCamera *cam, const B200rtRenderOpts *opts, float *out_rgb_device,
                          void *stream, B200rtStats *stats) {
     SceneImpl *s = as_scene(scene);

@@ -31,6 +31,48 @@ __global__ void __launch_bounds__(128) raycast_kernel(DeviceScene S, const doubl
     }
 }
 
+// One surface interaction per ray with the CALLER's random words: closest hit, then shade_hit -- the very
+// device function the path kernels call -- on a unit throughput.  Test hook (b200rt_debug_shade): makes the
+// hit_info face rule and the four materials checkable ray by ray against the oracle's reflected / refracted /
+// reflectance, which the path kernels' own Philox streams do not allow.
+struct ShadeRecord {
+    double scattered[6];   // origin, direction of the scattered ray (zeros if the path ended)
+    double t;
+    float atten[3];        // throughput after the interaction (the material's attenuation)
+    float emit[3];         // emitted radiance picked up at the hit
+    int32_t prim;          // canonical primitive index or -1
+    int32_t flags;         // bit 0: a scattered ray continues
+};
+static_assert(sizeof(ShadeRecord) == 88, "ShadeRecord is mirrored by numpy in capi.py");
+
+template <int STACK>
+__global__ void __launch_bounds__(128) debug_shade_kernel(DeviceScene S, const double *__restrict__ rays,
+                                                          const uint32_t *__restrict__ rnd, long long n, double tmin, double tmax,
+                                                          ShadeRecord *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray r{rays[i * 6 + 0], rays[i * 6 + 1], rays[i * 6 + 2], rays[i * 6 + 3], rays[i * 6 + 4], rays[i * 6 + 5]};
+    const Hit h = closest_hit<STACK, false>(S, r.ox, r.oy, r.oz, r.dx, r.dy, r.dz, tmin, tmax, nullptr);
+    ShadeRecord rec{};
+    rec.prim = -1;
+    if (h.ref != kNoHit) {
+        const Philox4 w{rnd[i * 4 + 0], rnd[i * 4 + 1], rnd[i * 4 + 2], rnd[i * 4 + 3]};
+        PathState p{1.0f, 1.0f, 1.0f};
+        float er = 0.0f, eg = 0.0f, eb = 0.0f;
+        const bool cont = shade_hit(S, h, w, r, p, er, eg, eb);
+        rec.prim = (int32_t)canonical_prim(S, h.ref);
+        rec.t = h.t;
+        rec.flags = cont ? 1 : 0;
+        if (cont) {
+            rec.scattered[0] = r.ox; rec.scattered[1] = r.oy; rec.scattered[2] = r.oz;
+            rec.scattered[3] = r.dx; rec.scattered[4] = r.dy; rec.scattered[5] = r.dz;
+            rec.atten[0] = p.tr; rec.atten[1] = p.tg; rec.atten[2] = p.tb;
+        }
+        rec.emit[0] = er; rec.emit[1] = eg; rec.emit[2] = eb;
+    }
+    out[i] = rec;
+}
+
 // ------------------------------------------------------------------------------------------
 // Thread -> pixel: a block is an 8x8 pixel tile, each warp an 8x4 sub-tile, so the 32 primary
 // rays of a warp are neighbours on the image plane.
@@ -305,6 +347,17 @@ cudaError_t launch_raycast(int stack, const DeviceScene &S, const double *rays, 
     if (stack <= 32) return launch_raycast_t<32>(S, rays, n, tmin, tmax, prim, t, st);
     if (stack <= 64) return launch_raycast_t<64>(S, rays, n, tmin, tmax, prim, t, st);
     return launch_raycast_t<128>(S, rays, n, tmin, tmax, prim, t, st);
+}
+
+cudaError_t launch_debug_shade(int stack, const DeviceScene &S, const double *rays, const uint32_t *rnd, long long n, double tmin,
+                               double tmax, void *records, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)((n + 127) / 128);
+    ShadeRecord *out = static_cast<ShadeRecord *>(records);
+    if (stack <= 32) debug_shade_kernel<32><<<blocks, 128, 0, st>>>(S, rays, rnd, n, tmin, tmax, out);
+    else if (stack <= 64) debug_shade_kernel<64><<<blocks, 128, 0, st>>>(S, rays, rnd, n, tmin, tmax, out);
+    else debug_shade_kernel<128><<<blocks, 128, 0, st>>>(S, rays, rnd, n, tmin, tmax, out);
+    return cudaGetLastError();
 }
 
 template <int STACK>

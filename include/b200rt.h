@@ -156,6 +156,24 @@ int b200rt_camera_init(B200rtCamera *cam);
 int b200rt_raycast(void *scene, const double *rays, int64_t n, double tmin, double tmax,
                    int32_t *prim_out, double *t_out);
 
+/* Test hook: ONE surface interaction per ray, performed by the same device function the path kernels
+ * call -- closest hit (as b200rt_raycast), hit point, the hit_info face rule (hittable.h:46-71), then
+ * Lambertian / Metal / Dielectric / DiffuseLight scatter + emit (material.h:64-263, vec3d.h:144-200) on a
+ * unit throughput -- but with the caller's four 32-bit random words per ray in place of the kernel's
+ * Philox stream, so each branch can be checked deterministically.  Word use: Lambertian and Metal
+ * sample the unit sphere from words 0,1 (u = (w >> 8) / 2^24; z = 1 - 2 u0, azimuth 2 pi u1); Dielectric
+ * compares u(word 2) with the Schlick reflectance (no word is used under total internal reflection). */
+typedef struct B200rtShadeRecord {
+    double scattered[6];   /* origin (= hit point) and unnormalised direction of the scattered ray; zeros if none */
+    double t;              /* hit time */
+    float atten[3];        /* attenuation applied (1,1,1 for Dielectric); zeros if the path ended */
+    float emit[3];         /* emitted radiance (DiffuseLight: intensity * colour, both faces) */
+    int32_t prim;          /* canonical primitive index, -1 = miss */
+    int32_t flags;         /* bit 0: scattered ray present */
+} B200rtShadeRecord;
+int b200rt_debug_shade(void *scene, const double *rays, const uint32_t *rnd, int64_t n, double tmin, double tmax,
+                       B200rtShadeRecord *records_out);
+
 /* ---- render ---------------------------------------------------------------------------- */
 /* Replaces: Camera::render<BVH>(bvh) (camera.h:264-297): for every pixel, the mean (or sum)
  * over the requested samples of ray_color (camera.h:205-258).  out_rgb = image_h x image_w x 3
