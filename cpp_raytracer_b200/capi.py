@@ -89,6 +89,7 @@ EXPORTS = {
                                       C.c_void_p, C.POINTER(Stats), C.POINTER(SceneInfo)]),
     "b200rt_tonemap": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "b200rt_tonemap_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "b200rt_debug_camera_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "b200rt_debug_shade": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
     "b200rt_finalize_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200rt_finalize_peers_device": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_double, C.c_void_p,
@@ -263,6 +264,17 @@ def render_scene(scene: HostScene, cam: np.ndarray, seed: int = 0xB200, sample_o
     _check(lib().b200rt_render_scene(C.byref(desc), cam.ctypes.data, C.byref(opts), None, out.ctypes.data,
                                      C.byref(st), C.byref(info)))
     return out, st.as_dict(), info.as_dict()
+
+
+def debug_camera_rays(cam: np.ndarray, pixels_xy: np.ndarray, rnd: np.ndarray, device: int = 0) -> np.ndarray:
+    """The kernels' primary rays for the given (col, row) pixels and random words (b200rt_debug_camera_rays)."""
+    cam = np.ascontiguousarray(cam, dtype=CAMERA_DTYPE).reshape(1)
+    pixels_xy = np.ascontiguousarray(pixels_xy, dtype=np.uint32).reshape(-1, 2)
+    rnd = np.ascontiguousarray(rnd, dtype=np.uint32).reshape(-1, 4)
+    out = np.empty((pixels_xy.shape[0], 6), dtype=np.float64)
+    _check(lib().b200rt_debug_camera_rays(cam.ctypes.data, pixels_xy.ctypes.data, rnd.ctypes.data, pixels_xy.shape[0],
+                                          out.ctypes.data, device))
+    return out
 
 
 def tonemap(hdr: np.ndarray, clamp: bool = False) -> np.ndarray:

@@ -564,6 +564,30 @@ int b200rt_raycast(void *scene, const double *rays, int64_t n, double tmin, doub
     return B200RT_OK;
 }
 
+int b200rt_debug_camera_rays(const B200rtCamera *cam, const uint32_t *pixels_xy, const uint32_t *rnd, int64_t n, double *rays_out,
+                             int device) {
+    CameraParams C{};
+    if (int rc = fill_camera(cam, C)) return rc;
+    if (n < 0 || (n && (!pixels_xy || !rnd || !rays_out))) return fail(B200RT_EINVAL, "bad debug_camera_rays buffers");
+    if (device_count_quiet() == 0) return fail(B200RT_ENODEVICE, "no CUDA device: libb200rt has no CPU path");
+    if (n == 0) return B200RT_OK;
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; } }
+    DeviceGuard g(device);
+    uint32_t *d_pix = nullptr, *d_rnd = nullptr;
+    double *d_rays = nullptr;
+    cudaError_t e = dev_alloc(&d_pix, (size_t)n * 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = dev_alloc(&d_rnd, (size_t)n * 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = dev_alloc(&d_rays, (size_t)n * 6 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(d_pix, pixels_xy, (size_t)n * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(d_rnd, rnd, (size_t)n * 4 * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_debug_camera(C, d_pix, d_rnd, n, d_rays, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(rays_out, d_rays, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaStreamSynchronize(0);
+    dev_free(d_pix); dev_free(d_rnd); dev_free(d_rays);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, std::string("debug_camera_rays: ") + cudaGetErrorString(e)); }
+    return B200RT_OK;
+}
+
 int b200rt_debug_shade(void *scene, const double *rays, const uint32_t *rnd, int64_t n, double tmin, double tmax,
                        B200rtShadeRecord *records_out) {
     static_assert(sizeof(B200rtShadeRecord) == 88, "record layout is shared with kernels.cu");

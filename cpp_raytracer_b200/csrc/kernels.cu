@@ -45,6 +45,20 @@ struct ShadeRecord {
 };
 static_assert(sizeof(ShadeRecord) == 88, "ShadeRecord is mirrored by numpy in capi.py");
 
+// Primary rays for given pixels with the CALLER's random words (test hook b200rt_debug_camera_rays): the
+// kernels' camera_ray, checkable against Camera::random_ray_through_pixel draw for draw.
+__global__ void debug_camera_kernel(const __grid_constant__ CameraParams C, const uint32_t *__restrict__ pixels,
+                                    const uint32_t *__restrict__ rnd, long long n, double *__restrict__ rays_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Philox4 w{rnd[i * 4 + 0], rnd[i * 4 + 1], rnd[i * 4 + 2], rnd[i * 4 + 3]};
+    Ray r;
+    PathState p;
+    camera_ray(C, pixels[i * 2 + 0], pixels[i * 2 + 1], w, r, p);
+    double *o = rays_out + i * 6;
+    o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; o[3] = r.dx; o[4] = r.dy; o[5] = r.dz;
+}
+
 template <int STACK>
 __global__ void __launch_bounds__(128) debug_shade_kernel(DeviceScene S, const double *__restrict__ rays,
                                                           const uint32_t *__restrict__ rnd, long long n, double tmin, double tmax,
@@ -347,6 +361,13 @@ cudaError_t launch_raycast(int stack, const DeviceScene &S, const double *rays, 
     if (stack <= 32) return launch_raycast_t<32>(S, rays, n, tmin, tmax, prim, t, st);
     if (stack <= 64) return launch_raycast_t<64>(S, rays, n, tmin, tmax, prim, t, st);
     return launch_raycast_t<128>(S, rays, n, tmin, tmax, prim, t, st);
+}
+
+cudaError_t launch_debug_camera(const CameraParams &C, const uint32_t *pixels, const uint32_t *rnd, long long n, double *rays_out,
+                                cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    debug_camera_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(C, pixels, rnd, n, rays_out);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_debug_shade(int stack, const DeviceScene &S, const double *rays, const uint32_t *rnd, long long n, double tmin,

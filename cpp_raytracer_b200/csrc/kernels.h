@@ -62,6 +62,8 @@ cudaError_t launch_raycast(int stack, const DeviceScene &S, const double *rays, 
 cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool voted, cudaStream_t st);
 cudaError_t launch_finalize(float *frame, long long n_pixels, float scale, int32_t *ldr, int clamp, cudaStream_t st);
 cudaError_t launch_tonemap(const float *hdr, long long n_pixels, int32_t *out, int clamp, cudaStream_t st);
+cudaError_t launch_debug_camera(const CameraParams &C, const uint32_t *pixels, const uint32_t *rnd, long long n, double *rays_out,
+                                cudaStream_t st);
 // records: n x 88-byte ShadeRecord (kernels.cu)
 cudaError_t launch_debug_shade(int stack, const DeviceScene &S, const double *rays, const uint32_t *rnd, long long n, double tmin,
                                double tmax, void *records, cudaStream_t st);

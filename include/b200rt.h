@@ -174,6 +174,13 @@ typedef struct B200rtShadeRecord {
 int b200rt_debug_shade(void *scene, const double *rays, const uint32_t *rnd, int64_t n, double tmin, double tmax,
                        B200rtShadeRecord *records_out);
 
+/* Test hook: the kernels' primary-ray construction (Camera::random_ray_through_pixel, camera.h:184-200, defocus
+ * disk camera.h:160-168) for n pixels (pixels_xy = n x {col, row}) with the caller's four random words per ray
+ * (u = (w >> 8) / 2^24): words 0,1 -> the U(-0.5,0.5) factors of delta_x, delta_y; words 2,3 -> the point in the
+ * unit disk (radius sqrt(u2), azimuth 2 pi u3), used only when defocus_angle > 0.  rays_out = n x 6 doubles. */
+int b200rt_debug_camera_rays(const B200rtCamera *cam, const uint32_t *pixels_xy, const uint32_t *rnd, int64_t n,
+                             double *rays_out, int device);
+
 /* ---- render ---------------------------------------------------------------------------- */
 /* Replaces: Camera::render<BVH>(bvh) (camera.h:264-297): for every pixel, the mean (or sum)
  * over the requested samples of ray_color (camera.h:205-258).  out_rgb = image_h x image_w x 3

@@ -257,35 +257,46 @@ static RGBd ray_color(RenderCtx *cx, V3 o, V3 d, uint64_t depth_left) {
     return rgb(emitted.r + att.r * in.r, emitted.g + att.g * in.g, emitted.b + att.b * in.b);   /* :233-234 */
 }
 
+/* camera.h:184-200 with the random draws supplied: (vx, vy) = the accepted point in the unit disk (vec3d.h:79-85;
+ * ignored for a pinhole camera), r1 / r2 = the U(-0.5, 0.5) factors of delta_x / delta_y.  Used by oracle_render
+ * below, so the bit-exact render test pins it against the reference. */
+void oracle_camera_ray(const OCamera *c, uint64_t row, uint64_t col, double vx, double vy, double r1, double r2, double out[6]) {
+    V3 center = from(c->center), p00 = from(c->pixel00), dx = from(c->delta_x), dy = from(c->delta_y);
+    V3 kx = from(c->disk_x), ky = from(c->disk_y);
+    V3 o = center;
+    if (!(c->defocus_angle <= 0)) o = vadd(vadd(center, vmul(kx, vx)), vmul(ky, vy));        /* camera.h:167 */
+    V3 pc = vadd(vadd(p00, vmul(dy, (double)row)), vmul(dx, (double)col));
+    V3 ps = vadd(vadd(pc, vmul(dx, r1)), vmul(dy, r2));
+    V3 d = vsub(ps, o);
+    out[0] = o.x; out[1] = o.y; out[2] = o.z; out[3] = d.x; out[4] = d.y; out[5] = d.z;
+}
+
 uint64_t oracle_render(const OScene *scene, const OCamera *c, uint32_t *lcg_state, double *out) {
     RenderCtx cx;
     cx.s = scene; cx.po = prim_order(scene); cx.rng = lcg_state; cx.rays = 0;
     cx.background = rgb(c->background[0], c->background[1], c->background[2]);
-    V3 center = from(c->center), p00 = from(c->pixel00), dx = from(c->delta_x), dy = from(c->delta_y);
-    V3 kx = from(c->disk_x), ky = from(c->disk_y);
     for (uint64_t row = 0; row < c->image_h; ++row) {                            /* camera.h:280-293 */
         for (uint64_t col = 0; col < c->image_w; ++col) {
             RGBd px = rgb(0, 0, 0);
             for (uint64_t s = 0; s < c->spp; ++s) {
-                V3 o = center;                                                   /* camera.h:184-200 */
+                V3 v = {0, 0, 0};                                                /* camera.h:184-200 */
                 if (!(c->defocus_angle <= 0)) {
-                    V3 v;                                                        /* vec3d.h:79-85 */
-                    do {
+                    do {                                                         /* vec3d.h:79-85 */
                         v.x = oracle_rand_double(cx.rng, -1, 1);
                         v.y = oracle_rand_double(cx.rng, -1, 1);
                         v.z = 0;
                     } while (!(vmag2(v) < 1));
-                    o = vadd(vadd(center, vmul(kx, v.x)), vmul(ky, v.y));        /* camera.h:167 */
                 }
-                V3 pc = vadd(vadd(p00, vmul(dy, (double)row)), vmul(dx, (double)col));
                 /* camera.h:197-198: `pc + rand*dx + rand*dy` -- the two draws are unsequenced in C++;
                  * g++ 13 (the compiler the reference is built with here) evaluates the right-hand
                  * operand first, i.e. the delta_y factor is drawn BEFORE the delta_x factor.  Pinned by
                  * the bit-exact render test. */
                 double r2 = oracle_rand_double(cx.rng, -0.5, 0.5);
                 double r1 = oracle_rand_double(cx.rng, -0.5, 0.5);
-                V3 ps = vadd(vadd(pc, vmul(dx, r1)), vmul(dy, r2));
-                RGBd col_s = ray_color(&cx, o, vsub(ps, o), c->max_depth);
+                double ray[6];
+                oracle_camera_ray(c, row, col, v.x, v.y, r1, r2, ray);
+                V3 o = {ray[0], ray[1], ray[2]}, ps_minus_o = {ray[3], ray[4], ray[5]};
+                RGBd col_s = ray_color(&cx, o, ps_minus_o, c->max_depth);
                 px.r += col_s.r; px.g += col_s.g; px.b += col_s.b;
             }
             double inv = 1 / (double)c->spp;                                     /* rgb.h:76: /= multiplies by 1/d */

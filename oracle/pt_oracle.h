@@ -43,6 +43,7 @@ double oracle_reflectance(double cos_theta, double ratio);
 
 /* camera.h:184-297 single-threaded, starting from the given per-thread LCG state; returns the
  * number of hit_by calls; writes image_h*image_w*3 doubles (linear HDR) and the final state. */
+void oracle_camera_ray(const OCamera *cam, uint64_t row, uint64_t col, double vx, double vy, double r1, double r2, double out[6]);
 uint64_t oracle_render(const OScene *scene, const OCamera *cam, uint32_t *lcg_state, double *out_rgb);
 
 /* rgb.h:90-113 */

@@ -43,6 +43,8 @@ def lib():
         l.oracle_reflectance.argtypes = [C.c_double, C.c_double]
         l.oracle_render.restype = C.c_uint64
         l.oracle_render.argtypes = [C.POINTER(OScene), C.c_void_p, C.POINTER(C.c_uint32), C.c_void_p]
+        l.oracle_camera_ray.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        l.oracle_camera_ray.restype = None
         l.oracle_tonemap.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
         _lib = l
     return _lib
@@ -102,6 +104,14 @@ def refracted(d, n, ratio):
 
 def reflectance(c, ratio):
     return lib().oracle_reflectance(c, ratio)
+
+
+def camera_ray(cam, row: int, col: int, vx: float, vy: float, r1: float, r2: float):
+    """random_ray_through_pixel (camera.h:184-200) with the draws supplied; cam must be initialised."""
+    cam = np.ascontiguousarray(cam).reshape(1)
+    out = np.empty(6)
+    lib().oracle_camera_ray(cam.ctypes.data, row, col, vx, vy, r1, r2, out.ctypes.data)
+    return out
 
 
 def render(scene, cam, lcg_state: int):

@@ -158,3 +158,38 @@ def test_one_surface_interaction_per_ray_matches_oracle(golden, name):
             assert seen[key] > 0, (key, seen)
     if name == "cornell":
         assert seen["lambert"] > 0 and seen["light"] > 0
+
+
+@pytest.mark.parametrize("name", ["rtow_lights", "rtow_final", "cornell", "xmas"])
+def test_primary_rays_match_oracle_draw_for_draw(golden, name):
+    """camera_ray on the device vs the oracle's random_ray_through_pixel (camera.h:184-200; pinned bit-exactly
+    against the reference by the single-thread render test) fed the same draws.  Pinhole cameras: bit-exact.
+    Defocus: the disk point is an FP32 sqrt / sincospif product on the device, so the origin agrees to 1e-6 of
+    the disk radius and the direction follows (target point bit-exact)."""
+    from cpp_raytracer_b200 import capi
+    import pt_oracle
+    scene = golden.scene(name)
+    cam = scene.camera.copy()
+    w, h = int(cam["image_w"][0]), int(cam["image_h"][0])
+    rng = np.random.default_rng(99)
+    n = 4000
+    pix = np.stack([rng.integers(0, w, n), rng.integers(0, h, n)], axis=1).astype(np.uint32)
+    pix[:4] = [[0, 0], [w - 1, 0], [0, h - 1], [w - 1, h - 1]]
+    rnd = rng.integers(0, 2 ** 32, size=(n, 4), dtype=np.uint32)
+    rnd[0] = 0
+    rnd[1] = 0xFFFFFFFF
+    got = capi.debug_camera_rays(cam, pix, rnd)
+    defocus = float(cam["defocus_angle"][0]) > 0
+    disk = max(np.linalg.norm(cam["disk_x"][0]), np.linalg.norm(cam["disk_y"][0]))
+    for i in range(n):
+        u = [np.float32(int(x) >> 8) * np.float32(1.0 / 16777216.0) for x in rnd[i]]
+        r1, r2 = float(u[0]) - 0.5, float(u[1]) - 0.5
+        rad = np.sqrt(u[2], dtype=np.float32)
+        ang = 2.0 * float(u[3]) * np.pi
+        vx, vy = float(rad) * np.cos(ang), float(rad) * np.sin(ang)
+        want = pt_oracle.camera_ray(cam, int(pix[i, 1]), int(pix[i, 0]), vx, vy, r1, r2)
+        if not defocus:
+            assert np.array_equal(got[i], want), (i, got[i], want)
+        else:
+            assert np.allclose(got[i, :3], want[:3], rtol=0, atol=2e-6 * disk + 1e-15)
+            assert np.allclose(got[i, :3] + got[i, 3:], want[:3] + want[3:], rtol=1e-15, atol=1e-15)   # the target point
