@@ -217,18 +217,6 @@ __device__ __forceinline__ void trav_pop(Trav &T, const uint2 *stack) {
     }
 }
 
-// child[key & 3] without branches (the compiler's version of the ?: chain branches, and lanes of a warp
-// then serialise over up to four sub-paths per pushed entry).
-__device__ __forceinline__ uint32_t pick_child(const int4 &ch, uint32_t key) {
-    uint32_t r;
-    asm("{\n\t.reg .pred p0, p1;\n\t.reg .b32 lo, hi, b;\n\t"
-        "and.b32 b, %5, 1;\n\tsetp.ne.u32 p0, b, 0;\n\t"
-        "and.b32 b, %5, 2;\n\tsetp.ne.u32 p1, b, 0;\n\t"
-        "selp.b32 lo, %2, %1, p0;\n\tselp.b32 hi, %4, %3, p0;\n\tselp.b32 %0, hi, lo, p1;\n\t}"
-        : "=r"(r) : "r"(ch.x), "r"(ch.y), "r"(ch.z), "r"(ch.w), "r"(key));
-    return r;
-}
-
 // One interior node: conservative FP32 slab tests of its four child boxes, nearest-first order.
 __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, uint2 *stack) {
     // Nodes are 128-byte aligned (checked at scene creation), so the six plane addresses are formed without
@@ -239,7 +227,6 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, ui
     const float4 bnx = B200RT_NODE_F4(pnx), bfx = B200RT_NODE_F4(pnx ^ 16);
     const float4 bny = B200RT_NODE_F4(pny), bfy = B200RT_NODE_F4(pny ^ 16);
     const float4 bnz = B200RT_NODE_F4(pnz), bfz = B200RT_NODE_F4(pnz ^ 16);
-    const int4 ch = __ldg(reinterpret_cast<const int4 *>(base + 96));
 #undef B200RT_NODE_F4
 #define B200RT_SLOT(c, k)                                                                                        \
     uint32_t key##k;                                                                                             \
@@ -248,7 +235,8 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, ui
                                fmaxf(__fmaf_rn(bnz.c, T.fiz, -T.cnz), T.tmin32));                                 \
         const float tf = fminf(fminf(__fmaf_rn(bfx.c, T.fix, -T.cfx), __fmaf_rn(bfy.c, T.fiy, -T.cfy)),             \
                                fminf(__fmaf_rn(bfz.c, T.fiz, -T.cfz), T.tmax32));                                 \
-        key##k = (tn <= tf * kBoxSlack) ? ((__float_as_uint(tn) & ~3u) | k) : 0xFFFFFFFFu;                        \
+        const uint32_t tag##k = (tn <= tf * kBoxSlack) ? (uint32_t)k : 0xFFFFFFFFu;   /* slot, or all ones = miss */  \
+        key##k = (__float_as_uint(tn) & ~3u) | tag##k;                                                           \
     }
     B200RT_SLOT(x, 0) B200RT_SLOT(y, 1) B200RT_SLOT(z, 2) B200RT_SLOT(w, 3)
 #undef B200RT_SLOT
@@ -257,7 +245,11 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, ui
     // unchanged within 0.2 %, but 2-3 % slower -- four predicated pushes cost more than the network.)
     B200RT_CSWAP(key0, key1) B200RT_CSWAP(key2, key3) B200RT_CSWAP(key0, key2)
     B200RT_CSWAP(key1, key3) B200RT_CSWAP(key1, key2)
-#define B200RT_CHILD(key) pick_child(ch, key)
+    // The child reference of a slot is FETCHED from the node just read (an L1 hit) rather than selected from
+    // four registers: selection is 5 ALU-pipe operations per pushed entry (or a branchy ?: chain on which the
+    // lanes of a warp serialise), and the node step is bound by the ALU pipe (88 of its ~150 instructions;
+    // the pipe issues one warp instruction every 2 cycles), not by the load/store unit.
+#define B200RT_CHILD(key) __ldg(reinterpret_cast<const uint32_t *>((base | (uint32_t)(((key) << 2) & 0xCu)) + 96))
     if (key0 != 0xFFFFFFFFu) {
         if (key3 != 0xFFFFFFFFu) stack[T.sp++] = make_uint2(B200RT_CHILD(key3), key3);
         if (key2 != 0xFFFFFFFFu) stack[T.sp++] = make_uint2(B200RT_CHILD(key2), key2);
