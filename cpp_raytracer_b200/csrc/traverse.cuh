@@ -149,7 +149,7 @@ struct Trav {
     float cnx, cny, cnz;             // o * (1/d), rounded UP   (+ pad): t_near = near_plane * inv - cn
     float cfx, cfy, cfz;             // o * (1/d), rounded DOWN (- pad): t_far  = far_plane  * inv - cf
     float tmin32, tmax32;
-    int nearx, neary, nearz;         // which float4 of a node is the near plane per axis
+    volatile uint32_t near_off[3];   // byte offset of the near-plane float4 of a node per axis; LOCAL MEMORY on purpose
     int sp;
     uint32_t cur;                    // interior node index | leaf reference | kTravDone
 };
@@ -197,7 +197,7 @@ __device__ __forceinline__ void trav_init(Trav &T, double ox, double oy, double 
     trav_axis(ox, dx, T.fix, T.cnx, T.cfx);
     trav_axis(oy, dy, T.fiy, T.cny, T.cfy);
     trav_axis(oz, dz, T.fiz, T.cnz, T.cfz);
-    T.nearx = T.fix < 0.0f ? 1 : 0; T.neary = T.fiy < 0.0f ? 3 : 2; T.nearz = T.fiz < 0.0f ? 5 : 4;
+    T.near_off[0] = T.fix < 0.0f ? 16u : 0u; T.near_off[1] = T.fiy < 0.0f ? 48u : 32u; T.near_off[2] = T.fiz < 0.0f ? 80u : 64u;
     T.tmin = tmin;
     T.tmin32 = float_toward(tmin, false);
     T.tmax32 = float_toward(tmax, true);
@@ -222,7 +222,7 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, ui
     // Nodes are 128-byte aligned (checked at scene creation), so the six plane addresses are formed without
     // carries: near = base | (0/16, 32/48, 64/80), far = near ^ 16 -- one logic op each on the low word.
     const uintptr_t base = reinterpret_cast<uintptr_t>(S.nodes) + ((uintptr_t)T.cur << 7);
-    const uintptr_t pnx = base | (uint32_t)(T.nearx << 4), pny = base | (uint32_t)(T.neary << 4), pnz = base | (uint32_t)(T.nearz << 4);
+    const uintptr_t pnx = base | T.near_off[0], pny = base | T.near_off[1], pnz = base | T.near_off[2];
 #define B200RT_NODE_F4(a) __ldg(reinterpret_cast<const float4 *>(a))
     const float4 bnx = B200RT_NODE_F4(pnx), bfx = B200RT_NODE_F4(pnx ^ 16);
     const float4 bny = B200RT_NODE_F4(pny), bfy = B200RT_NODE_F4(pny ^ 16);
