@@ -12,7 +12,11 @@ namespace b200rt {
 #endif
 constexpr int kPathBlock = B200RT_PATH_BLOCK;       // threads per block of the path kernels: an 8 x (kPathBlock/8) pixel tile
 constexpr int kPathTileH = kPathBlock / 8;
+#ifdef B200RT_PATH_MINB
+constexpr int kPathMinBlocks = B200RT_PATH_MINB;    // occupancy experiments
+#else
 constexpr int kPathMinBlocks = 1024 / kPathBlock;   // 1024 threads = 32 warps per SM at 64 registers
+#endif
 constexpr uint32_t kRenderAccumulate = 2u;   // == B200RT_FLAG_ACCUMULATE
 
 struct RenderParams {
