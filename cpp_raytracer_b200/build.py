@@ -53,8 +53,19 @@ def build_host(force: bool = False) -> str:
     return HOST_BIN
 
 
+FLAGS_STAMP = os.path.join(HERE, "build.flags")
+
+
+def _extra_flags() -> list:
+    return os.environ.get("B200RT_NVCC_EXTRA", "").split()   # experiment knob, e.g. -DB200RT_PATH_MINB=12
+
+
 def needs_build() -> bool:
     if not os.path.exists(LIB):
+        return True
+    # a library built with other experiment flags than the ones asked for now is stale too
+    built_with = open(FLAGS_STAMP).read().split() if os.path.exists(FLAGS_STAMP) else []
+    if built_with != _extra_flags():
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
@@ -65,7 +76,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = os.environ.get("B200RT_NVCC_EXTRA", "").split()   # experiment knob, e.g. -DB200RT_FULL_SORT
+    extra = _extra_flags()
     cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", LIB, *[os.path.join(CSRC, s) for s in SOURCES], "-lpthread"]
     env = dict(os.environ)
     env.pop("CXX", None)   # this image exports a CXX wrapper without libgomp specs
@@ -78,6 +89,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(log)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libb200rt.so (see cpp_raytracer_b200/build.log)")
+    with open(FLAGS_STAMP, "w") as f:
+        f.write(" ".join(extra))
     return LIB
 
 
