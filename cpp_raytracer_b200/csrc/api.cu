@@ -293,7 +293,7 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
         CUDA_TRY(run_wavefront(s->stack, P, W, (o.flags & B200RT_FLAG_COUNTERS) != 0, st, s->sm_count, &launches));
     } else {
         CUDA_TRY(launch_path_megakernel(s->stack, P, (o.flags & B200RT_FLAG_COUNTERS) != 0,
-                                        o.variant == B200RT_VARIANT_MEGAKERNEL_VOTED, st));
+                                        o.variant == B200RT_VARIANT_MEGAKERNEL_VOTED, s->info.tree_depth <= 3, st));
     }
     CUDA_TRY(cudaEventRecord(s->ev1, st));
     if (stats) {

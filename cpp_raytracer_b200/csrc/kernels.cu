@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(kPathBlock, kPathMinBlocks) path_megakernel_vo
 // path_megakernel (variant 0, default): every lane runs traverse-then-shade in a loop and starts
 // its next sample as soon as a path ends.  64 registers (16 blocks = 32 warps per SM) measured
 // fastest on B200: 8/12/16/20/24 blocks per SM gave 2707/3171/3263/2630/2307 Mpaths/s on C2.
-template <int STACK, bool COUNT, int MINB = kPathMinBlocks>
+template <int STACK, bool COUNT, bool SHALLOW = false, int MINB = kPathMinBlocks>
 __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel(const __grid_constant__ RenderParams P) {
     const CameraParams &C = P.cam;
     const PixelMap m = map_pixel(C);
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel(const __grid
     if (m.valid && C.max_depth > 0 && P.sample_count > 0) {
         while (shade_and_advance(P, m, best, L)) {
             // world.hit_by(ray, Interval::with_min(0.00001))  (camera.h:217)
-            best = closest_hit<STACK, COUNT>(P.scene, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001,
+            best = closest_hit<STACK, COUNT, SHALLOW>(P.scene, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001,
                                              __longlong_as_double(0x7ff0000000000000LL), &ctr);
         }
     }
@@ -382,11 +382,14 @@ cudaError_t launch_debug_shade(int stack, const DeviceScene &S, const double *ra
 }
 
 template <int STACK>
-static cudaError_t launch_path_t(const RenderParams &P, bool count, bool voted, cudaStream_t st) {
+static cudaError_t launch_path_t(const RenderParams &P, bool count, bool voted, bool shallow, cudaStream_t st) {
     const uint32_t tiles = ((P.cam.w + 7u) >> 3) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
     if (tiles == 0) return cudaSuccess;
     if (!voted) {
-        if (count) path_megakernel<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
+        if (STACK == 32 && shallow) {   // trees of depth <= 3 (a handful of nodes): while-while loop structure
+            if (count) path_megakernel<32, true, true><<<tiles, kPathBlock, 0, st>>>(P);
+            else path_megakernel<32, false, true><<<tiles, kPathBlock, 0, st>>>(P);
+        } else if (count) path_megakernel<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
         else path_megakernel<STACK, false><<<tiles, kPathBlock, 0, st>>>(P);
     } else {
         if (count) path_megakernel_voted<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
@@ -395,10 +398,10 @@ static cudaError_t launch_path_t(const RenderParams &P, bool count, bool voted, 
     return cudaGetLastError();
 }
 
-cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool voted, cudaStream_t st) {
-    if (stack <= 32) return launch_path_t<32>(P, count, voted, st);
-    if (stack <= 64) return launch_path_t<64>(P, count, voted, st);
-    return launch_path_t<128>(P, count, voted, st);
+cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool voted, bool shallow, cudaStream_t st) {
+    if (stack <= 32) return launch_path_t<32>(P, count, voted, shallow, st);
+    if (stack <= 64) return launch_path_t<64>(P, count, voted, false, st);
+    return launch_path_t<128>(P, count, voted, false, st);
 }
 
 cudaError_t launch_tonemap(const float *hdr, long long n_pixels, int32_t *out, int clamp, cudaStream_t st) {

@@ -291,13 +291,30 @@ __device__ __forceinline__ uint32_t trav_leaf_step(const DeviceScene &S, Trav &T
     return cnt;
 }
 
-template <int STACK, bool COUNT>
+// SHALLOW selects the loop structure.  Default: one step (node or leaf) per iteration, lanes re-converge every
+// iteration.  SHALLOW ("while-while"): consecutive node steps, then consecutive leaves; measured +9 % on the
+// Cornell box (tree of depth 3: 3.4 node steps and 1.8 FP64 quad tests per ray, so lanes at a leaf rarely wait
+// long for the others to leave the node loop) and -1 ... -18 % on the deeper trees of every other scene.
+template <int STACK, bool COUNT, bool SHALLOW = false>
 __device__ __forceinline__ Hit closest_hit(const DeviceScene &S, double ox, double oy, double oz,
                                            double dx, double dy, double dz, double tmin, double tmax,
                                            TraversalCounters *ctr) {
     Trav T;
     uint2 stack[STACK];
     trav_init(T, ox, oy, oz, dx, dy, dz, tmin, tmax);
+    if (SHALLOW) {
+        while (!trav_done(T)) {
+            while (trav_at_node(T)) {
+                if (COUNT) ctr->nodes++;
+                trav_node_step(S, T, stack);
+            }
+            while (trav_at_leaf(T)) {
+                const uint32_t c = trav_leaf_step(S, T, stack);
+                if (COUNT) ctr->prims += c;
+            }
+        }
+        return T.best;
+    }
     while (!trav_done(T)) {
         if (trav_at_node(T)) {
             if (COUNT) ctr->nodes++;
