@@ -154,3 +154,42 @@ def test_scene_file_roundtrip(golden, tmp_path):
     t = scene_io.load_scene(p)
     assert np.array_equal(s.spheres, t.spheres) and np.array_equal(s.quads, t.quads)
     assert np.array_equal(s.materials, t.materials) and s.camera.tobytes() == t.camera.tobytes()
+
+
+def test_header_is_plain_c_and_bindings_match_its_layout(tmp_path):
+    """include/b200rt.h compiled as C (gcc -std=c11 -pedantic): sizes and selected field offsets of every
+    struct, as the compiler lays them out, against the ctypes / numpy mirrors in capi.py."""
+    import subprocess
+    from cpp_raytracer_b200 import capi
+    structs = ["B200rtMaterial", "B200rtSphere", "B200rtQuad", "B200rtCamera", "B200rtSceneDesc", "B200rtBuildOpts",
+               "B200rtSceneInfo", "B200rtRenderOpts", "B200rtStats", "B200rtShadeRecord"]
+    offsets = [("B200rtShadeRecord", "t"), ("B200rtShadeRecord", "atten"), ("B200rtShadeRecord", "emit"),
+               ("B200rtShadeRecord", "prim"), ("B200rtShadeRecord", "flags"), ("B200rtCamera", "pixel00"),
+               ("B200rtCamera", "background"), ("B200rtSphere", "mat"), ("B200rtQuad", "mat"), ("B200rtMaterial", "param"),
+               ("B200rtStats", "paths"), ("B200rtSceneInfo", "build_ms"), ("B200rtRenderOpts", "flags")]
+    src = tmp_path / "layout.c"
+    body = "".join(f'    printf("sizeof {s} %zu\\n", sizeof({s}));\n' for s in structs)
+    body += "".join(f'    printf("offsetof {s}.{f} %zu\\n", offsetof({s}, {f}));\n' for s, f in offsets)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "b200rt.h"\nint main(void) {\n' + body + "    return 0;\n}\n")
+    exe = str(tmp_path / "layout")
+    env = dict(os.environ)
+    env.pop("CC", None); env.pop("CXX", None)
+    inc = os.path.join(ROOT, "include")
+    subprocess.run(["gcc", "-std=c11", "-pedantic", "-Wall", "-Werror", f"-I{inc}", "-o", exe, str(src)], check=True, env=env)
+    got = {}
+    for line in subprocess.run([exe], capture_output=True, text=True, check=True).stdout.splitlines():
+        kind, name, val = line.split()
+        got[(kind, name)] = int(val)
+    mirror = {"B200rtMaterial": capi.MATERIAL_DTYPE.itemsize, "B200rtSphere": capi.SPHERE_DTYPE.itemsize,
+              "B200rtQuad": capi.QUAD_DTYPE.itemsize, "B200rtCamera": capi.CAMERA_DTYPE.itemsize,
+              "B200rtSceneDesc": ctypes.sizeof(capi.SceneDesc), "B200rtBuildOpts": ctypes.sizeof(capi.BuildOpts),
+              "B200rtSceneInfo": ctypes.sizeof(capi.SceneInfo), "B200rtRenderOpts": ctypes.sizeof(capi.RenderOpts),
+              "B200rtStats": ctypes.sizeof(capi.Stats), "B200rtShadeRecord": capi.SHADE_RECORD_DTYPE.itemsize}
+    for s, size in mirror.items():
+        assert got[("sizeof", s)] == size, (s, got[("sizeof", s)], size)
+    np_of = {"B200rtShadeRecord": capi.SHADE_RECORD_DTYPE, "B200rtCamera": capi.CAMERA_DTYPE, "B200rtSphere": capi.SPHERE_DTYPE,
+             "B200rtQuad": capi.QUAD_DTYPE, "B200rtMaterial": capi.MATERIAL_DTYPE}
+    ct_of = {"B200rtStats": capi.Stats, "B200rtSceneInfo": capi.SceneInfo, "B200rtRenderOpts": capi.RenderOpts}
+    for s, f in offsets:
+        want = np_of[s].fields[f][1] if s in np_of else getattr(ct_of[s], f).offset
+        assert got[("offsetof", f"{s}.{f}")] == want, (s, f)
