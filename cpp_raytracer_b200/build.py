@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libb200rt.so")
-SOURCES = ["api.cu", "kernels.cu", "wavefront.cu", "lbvh.cu", "bvh_builder.cpp"]
-HEADERS = ["bvh_builder.h", "kernels.h", "thread_pool.h", "traverse.cuh", "shade.cuh", "rng.cuh",
+SOURCES = ["api.cu", "kernels.cu", "wavefront.cu", "lbvh.cu", "devmem.cu", "bvh_builder.cpp"]
+HEADERS = ["bvh_builder.h", "devmem.h", "kernels.h", "thread_pool.h", "traverse.cuh", "shade.cuh", "rng.cuh",
            os.path.join("..", "..", "include", "b200rt.h")]
 
 NVCC_FLAGS = [
@@ -72,6 +72,30 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+LIB_DBG = os.path.join(HERE, "libb200rt_dbg.so")
+
+
+def build_debug(force: bool = False) -> str:
+    """libb200rt_dbg.so: the same sources with -DB200RT_DEBUG_BOUNDS (every traversal-stack push, node / primitive /
+    material index and frame store range-checked on the device; b200rt_debug_bounds reports the counts).  The GPU
+    suite renders every scene through it (tests/test_gpu_bounds.py): the stand-in for compute-sanitizer, which
+    the GPU pool does not allow."""
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    if not force and os.path.exists(LIB_DBG) and all(os.path.getmtime(d) <= os.path.getmtime(LIB_DBG) for d in deps if os.path.exists(d)):
+        return LIB_DBG
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    flags = [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")]
+    cmd = [nvcc, *flags, "-DB200RT_DEBUG_BOUNDS", "-o", LIB_DBG, *[os.path.join(CSRC, s) for s in SOURCES], "-lpthread"]
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("nvcc failed building libb200rt_dbg.so")
+    return LIB_DBG
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
@@ -101,3 +125,4 @@ if __name__ == "__main__":
     a = ap.parse_args()
     print(build(force=a.force, verbose=a.verbose))
     print(build_host(force=a.force))
+    print(build_debug(force=a.force))

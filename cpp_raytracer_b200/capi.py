@@ -13,7 +13,9 @@ from dataclasses import dataclass
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200rt.so")
+# B200RT_LIB selects another build of the same library (the bounds-checked libb200rt_dbg.so the GPU suite runs
+# in place of compute-sanitizer); it must export the same ABI.
+LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(HERE, "libb200rt.so")
 
 # ---- struct dtypes (must mirror include/b200rt.h; checked against sizeof in tests) ---------
 MATERIAL_DTYPE = np.dtype([("kind", "<u4"), ("pad", "<u4"), ("rgb", "<f8", 3), ("param", "<f8")])
@@ -29,8 +31,8 @@ CAMERA_DTYPE = np.dtype([
 assert MATERIAL_DTYPE.itemsize == 40 and SPHERE_DTYPE.itemsize == 40 and QUAD_DTYPE.itemsize == 80
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_LIGHT = 0, 1, 2, 3
-VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT, VARIANT_MEGAKERNEL_VOTED = 0, 1, 2
-FLAG_SUM, FLAG_ACCUMULATE, FLAG_COUNTERS = 1, 2, 4
+VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1
+FLAG_SUM, FLAG_ACCUMULATE, FLAG_COUNTERS, FLAG_EXACT_COUNT = 1, 2, 4, 8
 BUILDER_AUTO, BUILDER_HOST_SAH, BUILDER_GPU_LBVH = 0, 1, 2
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, EINTERNAL = 0, -1, -2, -3, -4, -5
 
@@ -63,7 +65,9 @@ class RenderOpts(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("kernel_ms", C.c_double), ("h2d_ms", C.c_double), ("d2h_ms", C.c_double), ("total_ms", C.c_double),
                 ("paths", C.c_uint64), ("rays", C.c_uint64), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64),
-                ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
+                ("build_ms", C.c_double), ("replicate_ms", C.c_double), ("exchange_ms", C.c_double),
+                ("n_devices", C.c_uint32), ("peer_exchange", C.c_uint32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -78,7 +82,15 @@ EXPORTS = {
     "b200rt_device_count": (C.c_int, []),
     "b200rt_last_error": (C.c_char_p, []),
     "b200rt_version": (C.c_int, []),
+    "b200rt_trim": (C.c_int, []),
     "b200rt_scene_create": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(BuildOpts), C.POINTER(C.c_void_p)]),
+    "b200rt_scene_create_multi": (C.c_int, [C.POINTER(SceneDesc), C.POINTER(BuildOpts), C.POINTER(C.c_int32), C.c_int32,
+                                            C.POINTER(C.c_void_p)]),
+    "b200rt_render_scene_multi": (C.c_int, [C.POINTER(SceneDesc), C.c_void_p, C.POINTER(RenderOpts), C.POINTER(BuildOpts),
+                                            C.POINTER(C.c_int32), C.c_int32, C.c_void_p, C.POINTER(Stats), C.POINTER(SceneInfo)]),
+    "b200rt_debug_philox": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
+    "b200rt_debug_samplers": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int]),
+    "b200rt_debug_bounds": (C.c_int, [C.c_void_p, C.c_void_p]),
     "b200rt_scene_info": (C.c_int, [C.c_void_p, C.POINTER(SceneInfo)]),
     "b200rt_scene_destroy": (None, [C.c_void_p]),
     "b200rt_camera_init": (C.c_int, [C.c_void_p]),
@@ -91,6 +103,7 @@ EXPORTS = {
     "b200rt_tonemap_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200rt_debug_camera_rays": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int]),
     "b200rt_debug_shade": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_void_p]),
+    "b200rt_debug_lane_accounting": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(RenderOpts), C.c_void_p]),
     "b200rt_finalize_device": (C.c_int, [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "b200rt_finalize_peers_device": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_int64, C.c_double, C.c_void_p,
                                                C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
@@ -182,11 +195,18 @@ class DeviceSceneHandle:
     """Owns a b200rt scene handle (device-resident scene + BVH)."""
 
     def __init__(self, scene: HostScene, device: int = -1, max_leaf_prims: int = 0, sah_bins: int = 0, threads: int = 0,
-                 builder: int = BUILDER_AUTO):
+                 builder: int = BUILDER_AUTO, devices=None):
+        """`devices`: a list of CUDA ordinals makes the scene resident on all of them (b200rt_scene_create_multi:
+        built once on devices[0], copied to the others); render() then splits the samples across them."""
         self._h = C.c_void_p()
         desc = scene.desc()
-        bo = BuildOpts(device, max_leaf_prims, sah_bins, threads, builder)
-        _check(lib().b200rt_scene_create(C.byref(desc), C.byref(bo), C.byref(self._h)))
+        if devices is not None:
+            devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+            bo = BuildOpts(int(devices[0]) if len(devices) else -1, max_leaf_prims, sah_bins, threads, builder)
+            _check(lib().b200rt_scene_create_multi(C.byref(desc), C.byref(bo), devs, len(devices), C.byref(self._h)))
+        else:
+            bo = BuildOpts(device, max_leaf_prims, sah_bins, threads, builder)
+            _check(lib().b200rt_scene_create(C.byref(desc), C.byref(bo), C.byref(self._h)))
         self.host = scene
 
     def close(self):
@@ -240,6 +260,20 @@ class DeviceSceneHandle:
         _check(lib().b200rt_render(self._h, cam.ctypes.data, C.byref(opts), out.ctypes.data, C.byref(st)))
         return out, st.as_dict()
 
+    def bounds_violations(self) -> np.ndarray:
+        """[stack, node index, primitive / material index, pixel] violations counted by a -DB200RT_DEBUG_BOUNDS build."""
+        out = np.zeros(4, dtype=np.uint64)
+        _check(lib().b200rt_debug_bounds(self._h, out.ctypes.data))
+        return out
+
+    def lane_accounting(self, cam: np.ndarray, seed: int = 0xB200, sample_offset: int = 0, sample_count: int = 0) -> np.ndarray:
+        """Per-warp lane accounting of the default kernel's schedule (b200rt_debug_lane_accounting): 16 counters."""
+        cam = np.ascontiguousarray(cam, dtype=CAMERA_DTYPE).reshape(1)
+        opts = RenderOpts(seed, sample_offset, sample_count, 0, 0)
+        out = np.zeros(16, dtype=np.uint64)
+        _check(lib().b200rt_debug_lane_accounting(self._h, cam.ctypes.data, C.byref(opts), out.ctypes.data))
+        return out
+
     def render_device(self, cam: np.ndarray, out_ptr: int, stream: int = 0, seed: int = 0xB200, sample_offset: int = 0,
                       sample_count: int = 0, variant: int = VARIANT_MEGAKERNEL, flags: int = 0, want_stats: bool = True):
         """Renders into a DEVICE buffer (e.g. a torch tensor's data_ptr()) on `stream`."""
@@ -252,8 +286,9 @@ class DeviceSceneHandle:
 
 
 def render_scene(scene: HostScene, cam: np.ndarray, seed: int = 0xB200, sample_offset: int = 0, sample_count: int = 0,
-                 variant: int = VARIANT_MEGAKERNEL, flags: int = 0, out: np.ndarray | None = None):
-    """The one-call drop-in for Camera::render(const Scene&): build + upload + render + read back."""
+                 variant: int = VARIANT_MEGAKERNEL, flags: int = 0, out: np.ndarray | None = None, devices=None):
+    """The one-call drop-in for Camera::render(const Scene&): build + upload + render + read back.
+    `devices`: list of CUDA ordinals -> b200rt_render_scene_multi (sample split across them inside the library)."""
     cam = np.ascontiguousarray(cam, dtype=CAMERA_DTYPE).reshape(1)
     h, w = int(cam["image_h"][0]), int(cam["image_w"][0])
     if out is None:
@@ -261,9 +296,31 @@ def render_scene(scene: HostScene, cam: np.ndarray, seed: int = 0xB200, sample_o
     desc = scene.desc()
     opts = RenderOpts(seed, sample_offset, sample_count, variant, flags)
     st, info = Stats(), SceneInfo()
-    _check(lib().b200rt_render_scene(C.byref(desc), cam.ctypes.data, C.byref(opts), None, out.ctypes.data,
-                                     C.byref(st), C.byref(info)))
+    if devices is not None:
+        devs = (C.c_int32 * len(devices))(*[int(d) for d in devices])
+        _check(lib().b200rt_render_scene_multi(C.byref(desc), cam.ctypes.data, C.byref(opts), None, devs, len(devices),
+                                               out.ctypes.data, C.byref(st), C.byref(info)))
+    else:
+        _check(lib().b200rt_render_scene(C.byref(desc), cam.ctypes.data, C.byref(opts), None, out.ctypes.data,
+                                         C.byref(st), C.byref(info)))
     return out, st.as_dict(), info.as_dict()
+
+
+def debug_philox(counters_keys: np.ndarray, device: int = 0) -> np.ndarray:
+    """Philox4x32-10 as the kernels evaluate it, on the device: rows of (c0, c1, c2, c3, k0, k1) -> rows of 4 words."""
+    ck = np.ascontiguousarray(counters_keys, dtype=np.uint32).reshape(-1, 6)
+    out = np.empty((ck.shape[0], 4), dtype=np.uint32)
+    _check(lib().b200rt_debug_philox(ck.ctypes.data, ck.shape[0], out.ctypes.data, device))
+    return out
+
+
+def debug_samplers(rnd_pairs: np.ndarray, device: int = 0):
+    """The kernels' unit-sphere and unit-disk samplers for rows of two random words: (n x 3, n x 2) doubles."""
+    rnd = np.ascontiguousarray(rnd_pairs, dtype=np.uint32).reshape(-1, 2)
+    sph = np.empty((rnd.shape[0], 3), dtype=np.float64)
+    disk = np.empty((rnd.shape[0], 2), dtype=np.float64)
+    _check(lib().b200rt_debug_samplers(rnd.ctypes.data, rnd.shape[0], sph.ctypes.data, disk.ctypes.data, device))
+    return sph, disk
 
 
 def debug_camera_rays(cam: np.ndarray, pixels_xy: np.ndarray, rnd: np.ndarray, device: int = 0) -> np.ndarray:

@@ -12,11 +12,13 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/b200rt.h"
 #include "bvh_builder.h"
+#include "devmem.h"
 #include "kernels.h"
 #include "thread_pool.h"
 
@@ -61,55 +63,57 @@ struct DeviceGuard {
     ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
-// Device memory comes from the device's default stream-ordered pool with its release threshold
-// raised, so that the create / render / destroy cycle of the drop-in call (one per frame) reuses
-// memory instead of paying cudaMalloc / cudaFree (and their device-wide synchronisation) each time.
-cudaError_t dev_alloc(void **p, size_t bytes) {
-    static bool pool_ready[64] = {};
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e != cudaSuccess) return e;
-    if (dev >= 0 && dev < 64 && !pool_ready[dev]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        } else {
-            cudaGetLastError();
-        }
-        pool_ready[dev] = true;
-    }
-    e = cudaMallocAsync(p, bytes ? bytes : 1, 0);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
-    return e;
-}
-template <typename T>
-cudaError_t dev_alloc(T **p, size_t bytes) { return dev_alloc(reinterpret_cast<void **>(p), bytes); }
-void dev_free(void *p) {
-    if (p) cudaFreeAsync(p, 0);
-}
+constexpr uint32_t kSceneMagic = 0xB200577Eu, kMultiMagic = 0xB2003171u;
 
 struct SceneImpl {
-    uint32_t magic = 0xB200577Eu;
+    uint32_t magic = kSceneMagic;
     int device = 0;
+    std::mutex mu;                   // a handle is not re-entrant: calls on it are serialised
     DeviceScene d{};                 // device pointers
+    // [0] nodes, [1] spheres, [2] sphere_meta, [3] quads, [4] quad_meta, [5] materials
     void *allocs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t alloc_bytes[6] = {0, 0, 0, 0, 0, 0};
     B200rtSceneInfo info{};
     int stack = 32;
-    unsigned long long *d_counters = nullptr;
+    unsigned long long *d_counters = nullptr;   // [0] rays, [1] node visits, [2] primitive tests
+    unsigned long long *d_viol = nullptr;       // bounds-checked build only: [4] violation counters
     float *d_frame = nullptr;        // scratch frame for the host-buffer render entry
     size_t frame_floats = 0;
     double *d_rays = nullptr; int32_t *d_prim = nullptr; double *d_t = nullptr;   // raycast scratch
     size_t ray_capacity = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_pool = nullptr;   // wavefront: the path-slot pool is free again (renders of one scene share it)
     void *d_pool = nullptr;          // wavefront path-slot pool
     uint32_t pool_slots = 0;
     int sm_count = 148;
 };
 
+// The scene resident on several devices of this process (b200rt_scene_create_multi).
+struct MultiImpl {
+    uint32_t magic = kMultiMagic;
+    std::mutex mu;
+    std::vector<SceneImpl *> dev;            // dev[0] was built; the others are device-to-device copies of it
+    std::vector<cudaStream_t> stream;        // one non-blocking stream per device
+    std::vector<cudaEvent_t> ev_render, ev_xchg;
+    std::vector<float *> frame;              // per-device FP32 SUM frame
+    float *scratch = nullptr;                // devices[0]: landing buffer of the exchange without peer mapping
+    size_t frame_floats = 0;
+    bool peers = false;                      // every device can dereference every other device's pool memory
+    double replicate_ms = 0;
+};
+
 SceneImpl *as_scene(void *h) {
     SceneImpl *s = static_cast<SceneImpl *>(h);
-    return (s && s->magic == 0xB200577Eu) ? s : nullptr;
+    return (s && s->magic == kSceneMagic) ? s : nullptr;
+}
+MultiImpl *as_multi(void *h) {
+    MultiImpl *m = static_cast<MultiImpl *>(h);
+    return (m && m->magic == kMultiMagic) ? m : nullptr;
+}
+// the single-device scene behind either kind of handle (devices[0] of a multi-device one)
+SceneImpl *root_scene(void *h) {
+    if (MultiImpl *m = as_multi(h)) return m->dev.empty() ? nullptr : m->dev[0];
+    return as_scene(h);
 }
 
 int device_count_quiet() {
@@ -208,13 +212,14 @@ BuildParams build_params(const B200rtBuildOpts *o) {
 }
 
 template <typename T>
-int upload(const std::vector<T> &host, const T **dev, void **slot, uint64_t &bytes) {
+int upload(const std::vector<T> &host, const T **dev, void **slot, size_t *slot_bytes, uint64_t &bytes) {
     *dev = nullptr;
     if (host.empty()) return B200RT_OK;
     void *p = nullptr;
     CUDA_TRY(dev_alloc(&p, host.size() * sizeof(T)));
-    *slot = p;
-    CUDA_TRY(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *slot = p;                                     // owned by the scene from here on (freed by free_scene on any later failure)
+    *slot_bytes = host.size() * sizeof(T);
+    CUDA_TRY(staged_upload(p, host.data(), host.size() * sizeof(T), 0));
     *dev = static_cast<const T *>(p);
     bytes += host.size() * sizeof(T);
     return B200RT_OK;
@@ -226,6 +231,7 @@ void free_scene(SceneImpl *s) {
     cudaDeviceSynchronize();   // kernels of any stream may still read the scene
     for (void *&p : s->allocs) { dev_free(p); p = nullptr; }
     dev_free(s->d_counters);
+    dev_free(s->d_viol);
     dev_free(s->d_frame);
     dev_free(s->d_rays);
     dev_free(s->d_prim);
@@ -233,8 +239,26 @@ void free_scene(SceneImpl *s) {
     dev_free(s->d_pool);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev_pool) cudaEventDestroy(s->ev_pool);
     s->magic = 0;
     delete s;
+}
+
+void free_multi(MultiImpl *m) {
+    if (!m) return;
+    for (size_t i = 0; i < m->dev.size(); ++i) {
+        if (!m->dev[i]) continue;
+        DeviceGuard g(m->dev[i]->device);
+        if (i < m->stream.size() && m->stream[i]) cudaStreamSynchronize(m->stream[i]);
+        if (i < m->frame.size()) dev_free(m->frame[i]);
+        if (i == 0) dev_free(m->scratch);
+        if (i < m->ev_render.size() && m->ev_render[i]) cudaEventDestroy(m->ev_render[i]);
+        if (i < m->ev_xchg.size() && m->ev_xchg[i]) cudaEventDestroy(m->ev_xchg[i]);
+        if (i < m->stream.size() && m->stream[i]) cudaStreamDestroy(m->stream[i]);
+    }
+    for (SceneImpl *s : m->dev) free_scene(s);
+    m->magic = 0;
+    delete m;
 }
 
 int fill_camera(const B200rtCamera *cam, CameraParams &C) {
@@ -254,17 +278,25 @@ int fill_camera(const B200rtCamera *cam, CameraParams &C) {
     return B200RT_OK;
 }
 
+// Resolves the sample range of a render call: count 0 means camera.spp unless B200RT_FLAG_EXACT_COUNT is set.
+int sample_range_of(const B200rtCamera *cam, const B200rtRenderOpts &o, uint64_t *count_out) {
+    const uint64_t count = (o.sample_count || (o.flags & B200RT_FLAG_EXACT_COUNT)) ? o.sample_count : cam->spp;
+    if (count > 0xFFFFFFFFull || o.sample_offset + count > 0xFFFFFFFFull) return fail(B200RT_EINVAL, "sample range out of range");
+    if (o.variant != B200RT_VARIANT_MEGAKERNEL && o.variant != B200RT_VARIANT_WAVEFRONT)
+        return fail(B200RT_EINVAL, "unknown kernel variant");
+    *count_out = count;
+    return B200RT_OK;
+}
+
+// Enqueues the path kernel(s) of one render call on `st` (the caller holds s->mu and has made s->device current).
 int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOpts *opts, float *d_out,
                      cudaStream_t st, B200rtStats *stats, bool sync_for_stats) {
     RenderParams P{};
     if (int rc = fill_camera(cam, P.cam)) return rc;
     B200rtRenderOpts o{};
     if (opts) o = *opts;
-    const uint64_t count = o.sample_count ? o.sample_count : cam->spp;
-    if (count > 0xFFFFFFFFull || o.sample_offset + count > 0xFFFFFFFFull) return fail(B200RT_EINVAL, "sample range out of range");
-    if (o.variant != B200RT_VARIANT_MEGAKERNEL && o.variant != B200RT_VARIANT_MEGAKERNEL_VOTED &&
-        o.variant != B200RT_VARIANT_WAVEFRONT)
-        return fail(B200RT_EINVAL, "unknown kernel variant");
+    uint64_t count = 0;
+    if (int rc = sample_range_of(cam, o, &count)) return rc;
     P.scene = s->d;
     P.seed = o.seed;
     P.sample_begin = (uint32_t)o.sample_offset;
@@ -276,30 +308,38 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
     CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 3 * sizeof(unsigned long long), st));
     unsigned long long launches = 1;
     CUDA_TRY(cudaEventRecord(s->ev0, st));
-    if (o.variant == B200RT_VARIANT_WAVEFRONT) {
-        // pool of path slots: 2^21 by default (B200RT_WF_SLOTS overrides, for experiments)
+    if (count == 0) {
+        // an empty share of a sample split: no samples, so the sum is zero (nothing to add under ACCUMULATE)
+        launches = 0;
+        if (!(o.flags & B200RT_FLAG_ACCUMULATE))
+            CUDA_TRY(cudaMemsetAsync(d_out, 0, (size_t)cam->image_w * cam->image_h * 3 * sizeof(float), st));
+    } else if (o.variant == B200RT_VARIANT_WAVEFRONT) {
+        // pool of path slots: 2^21 by default (B200RT_WF_SLOTS overrides, for experiments).  Renders of one scene
+        // share the pool: each waits (on the device) for the previous one to be done with it.
         uint32_t want = 1u << 21;
         if (const char *e = std::getenv("B200RT_WF_SLOTS")) want = (uint32_t)std::max(1024ll, std::atoll(e));
         const unsigned long long items = (unsigned long long)cam->image_w * cam->image_h * count;
         if (items < want) want = (uint32_t)std::max(1024ull, items);
         if (want != s->pool_slots) {
-            if (s->d_pool) { cudaStreamSynchronize(st); dev_free(s->d_pool); s->d_pool = nullptr; s->pool_slots = 0; }
+            if (s->d_pool) { cudaEventSynchronize(s->ev_pool); dev_free(s->d_pool); s->d_pool = nullptr; s->pool_slots = 0; }
             CUDA_TRY(dev_alloc(&s->d_pool, wavefront_pool_alloc_bytes(want)));
             s->pool_slots = want;
         }
+        CUDA_TRY(cudaStreamWaitEvent(st, s->ev_pool, 0));
         WavefrontPool W{};
         wavefront_pool_layout(s->d_pool, s->pool_slots, W);
         launches = 0;
         CUDA_TRY(run_wavefront(s->stack, P, W, (o.flags & B200RT_FLAG_COUNTERS) != 0, st, s->sm_count, &launches));
+        CUDA_TRY(cudaEventRecord(s->ev_pool, st));
     } else {
-        CUDA_TRY(launch_path_megakernel(s->stack, P, (o.flags & B200RT_FLAG_COUNTERS) != 0,
-                                        o.variant == B200RT_VARIANT_MEGAKERNEL_VOTED, s->info.tree_depth <= 3, st));
+        CUDA_TRY(launch_path_megakernel(s->stack, P, (o.flags & B200RT_FLAG_COUNTERS) != 0, s->info.tree_depth <= 3, st));
     }
     CUDA_TRY(cudaEventRecord(s->ev1, st));
     if (stats) {
         std::memset(stats, 0, sizeof *stats);
         stats->paths = (uint64_t)cam->image_w * cam->image_h * count;
         stats->kernel_launches = launches;
+        stats->n_devices = 1;
         if (sync_for_stats) {
             unsigned long long c[3];
             CUDA_TRY(cudaMemcpyAsync(c, s->d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
@@ -376,13 +416,14 @@ int scene_build_host(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, S
     {
         std::vector<float4> flat(bvh.nodes.size() * 8);
         std::memcpy(flat.data(), bvh.nodes.data(), bvh.nodes.size() * sizeof(Node4));
-        rc = upload(flat, &d_nodes, &s->allocs[0], bytes);
+        rc = upload(flat, &d_nodes, &s->allocs[0], &s->alloc_bytes[0], bytes);
     }
-    if (!rc) rc = upload(sph, &s->d.spheres, &s->allocs[1], bytes);
-    if (!rc) rc = upload(sph_meta, &s->d.sphere_meta, &s->allocs[2], bytes);
-    if (!rc) rc = upload(quads, &s->d.quads, &s->allocs[3], bytes);
-    if (!rc) rc = upload(quad_meta, &s->d.quad_meta, &s->allocs[4], bytes);
-    if (!rc) rc = upload(mats, &s->d.materials, &s->allocs[5], bytes);
+    if (!rc) rc = upload(sph, &s->d.spheres, &s->allocs[1], &s->alloc_bytes[1], bytes);
+    if (!rc) rc = upload(sph_meta, &s->d.sphere_meta, &s->allocs[2], &s->alloc_bytes[2], bytes);
+    if (!rc) rc = upload(quads, &s->d.quads, &s->allocs[3], &s->alloc_bytes[3], bytes);
+    if (!rc) rc = upload(quad_meta, &s->d.quad_meta, &s->allocs[4], &s->alloc_bytes[4], bytes);
+    if (!rc) rc = upload(mats, &s->d.materials, &s->allocs[5], &s->alloc_bytes[5], bytes);
+    if (!rc && cudaStreamSynchronize(0) != cudaSuccess) rc = fail(B200RT_ECUDA, "scene upload failed");
     s->d.nodes = d_nodes;
     if (rc) return rc;
     if (reinterpret_cast<uintptr_t>(d_nodes) & 127)   // trav_node_step forms plane addresses with OR / XOR on the low bits
@@ -405,41 +446,44 @@ int scene_build_gpu(const B200rtSceneDesc *desc, SceneImpl *s, bool *too_deep) {
     *too_deep = false;
     const double t0 = now_ms();
     const uint32_t n_sph = (uint32_t)desc->n_spheres, n_quad = (uint32_t)desc->n_quads;
+    if (n_sph > kLeafIndexMask || n_quad > kLeafIndexMask || (uint64_t)n_sph + n_quad > (1u << 29))
+        return fail(B200RT_EINVAL, "too many primitives for the leaf encoding (2^26 per type)");
     uint64_t bytes = 0;
+    // The caller's structs go up as they are (pinned staging, pipelined); the scene's own arrays are allocated
+    // straight into s->allocs so that free_scene releases them on every failure path below.
     B200rtSphere *raw_sph = nullptr;
     B200rtQuad *raw_quad = nullptr;
-    auto drop_raw = [&]() { dev_free(raw_sph); dev_free(raw_quad); };
-    CUDA_TRY(dev_alloc(&raw_sph, (size_t)n_sph * sizeof(B200rtSphere)));
-    CUDA_TRY(dev_alloc(&raw_quad, (size_t)n_quad * sizeof(B200rtQuad)));
-    cudaError_t e = cudaSuccess;
-    if (n_sph) e = cudaMemcpy(raw_sph, desc->spheres, (size_t)n_sph * sizeof(B200rtSphere), cudaMemcpyHostToDevice);
-    if (e == cudaSuccess && n_quad) e = cudaMemcpy(raw_quad, desc->quads, (size_t)n_quad * sizeof(B200rtQuad), cudaMemcpyHostToDevice);
-    double2 *d_sph = nullptr, *d_quads = nullptr;
-    uint2 *d_sph_meta = nullptr, *d_quad_meta = nullptr;
-    if (e == cudaSuccess) e = dev_alloc(&d_sph, (size_t)n_sph * 2 * sizeof(double2));
-    s->allocs[1] = d_sph;
-    if (e == cudaSuccess) e = dev_alloc(&d_sph_meta, (size_t)n_sph * sizeof(uint2));
-    s->allocs[2] = d_sph_meta;
-    if (e == cudaSuccess) e = dev_alloc(&d_quads, (size_t)n_quad * 8 * sizeof(double2));
-    s->allocs[3] = d_quads;
-    if (e == cudaSuccess) e = dev_alloc(&d_quad_meta, (size_t)n_quad * sizeof(uint2));
-    s->allocs[4] = d_quad_meta;
+    struct RawGuard {
+        B200rtSphere *&a; B200rtQuad *&b;
+        ~RawGuard() { dev_free(a); dev_free(b); }
+    } raw_guard{raw_sph, raw_quad};
+    CUDA_TRY(dev_alloc_async(&raw_sph, (size_t)n_sph * sizeof(B200rtSphere), 0));
+    CUDA_TRY(dev_alloc_async(&raw_quad, (size_t)n_quad * sizeof(B200rtQuad), 0));
+    const size_t sizes[6] = {0, (size_t)n_sph * 2 * sizeof(double2), (size_t)n_sph * sizeof(uint2),
+                             (size_t)n_quad * 8 * sizeof(double2), (size_t)n_quad * sizeof(uint2), 0};
+    for (int i = 1; i <= 4; ++i) {
+        CUDA_TRY(dev_alloc_async(&s->allocs[i], sizes[i], 0));
+        s->alloc_bytes[i] = sizes[i];
+    }
+    CUDA_TRY(staged_upload(raw_sph, desc->spheres, (size_t)n_sph * sizeof(B200rtSphere), 0));
+    CUDA_TRY(staged_upload(raw_quad, desc->quads, (size_t)n_quad * sizeof(B200rtQuad), 0));
+    double2 *d_sph = static_cast<double2 *>(s->allocs[1]), *d_quads = static_cast<double2 *>(s->allocs[3]);
+    uint2 *d_sph_meta = static_cast<uint2 *>(s->allocs[2]), *d_quad_meta = static_cast<uint2 *>(s->allocs[4]);
     float4 *d_nodes = nullptr;
     uint32_t n_nodes = 0, depth = 0;
-    if (e == cudaSuccess)
-        e = build_lbvh_device(raw_sph, n_sph, raw_quad, n_quad, d_sph, d_sph_meta, d_quads, d_quad_meta, &d_nodes, &n_nodes, &depth);
-    s->allocs[0] = d_nodes;
-    drop_raw();
+    const cudaError_t e = build_lbvh_device(raw_sph, n_sph, raw_quad, n_quad, d_sph, d_sph_meta, d_quads, d_quad_meta, &d_nodes, &n_nodes, &depth);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, std::string("GPU BVH build: ") + cudaGetErrorString(e)); }
+    s->allocs[0] = d_nodes;
+    s->alloc_bytes[0] = (size_t)n_nodes * sizeof(Node4);
     if (3 * depth > 128) { *too_deep = true; return B200RT_OK; }
     const std::vector<DeviceMaterial> mats = device_materials(desc);
-    if (int rc = upload(mats, &s->d.materials, &s->allocs[5], bytes)) return rc;
+    if (int rc = upload(mats, &s->d.materials, &s->allocs[5], &s->alloc_bytes[5], bytes)) return rc;
     if (reinterpret_cast<uintptr_t>(d_nodes) & 127)   // trav_node_step forms plane addresses with OR / XOR on the low bits
         return fail(B200RT_ECUDA, "node array is not 128-byte aligned");
     s->d.nodes = d_nodes;
     s->d.spheres = d_sph; s->d.sphere_meta = d_sph_meta;
     s->d.quads = d_quads; s->d.quad_meta = d_quad_meta;
-    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaStreamSynchronize(0));
     bytes += (uint64_t)n_nodes * sizeof(Node4) + (uint64_t)n_sph * (2 * sizeof(double2) + sizeof(uint2)) +
              (uint64_t)n_quad * (8 * sizeof(double2) + sizeof(uint2));
     const int need_stack = (int)(3 * depth);
@@ -449,6 +493,214 @@ int scene_build_gpu(const B200rtSceneDesc *desc, SceneImpl *s, bool *too_deep) {
     s->info.tree_depth = depth;
     s->info.build_ms = now_ms() - t0;
     s->info.upload_ms = 0;
+    return B200RT_OK;
+}
+
+// Per-scene launch state (counters, events, the bounds-check table of the debug build); `s->device` is current.
+int finish_scene_setup(SceneImpl *s) {
+    cudaError_t e = dev_alloc(&s->d_counters, 3 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s->ev_pool, cudaEventDisableTiming);
+#ifdef B200RT_DEBUG_BOUNDS
+    if (e == cudaSuccess) e = dev_alloc(&s->d_viol, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_viol, 0, 4 * sizeof(unsigned long long), 0);
+    s->d.dbg.viol = s->d_viol;
+    s->d.dbg.n_nodes = (uint32_t)s->info.n_nodes;
+    s->d.dbg.n_spheres = (uint32_t)s->info.n_spheres;
+    s->d.dbg.n_quads = (uint32_t)s->info.n_quads;
+    s->d.dbg.n_materials = (uint32_t)s->info.n_materials;
+    s->d.dbg.stack_cap = (uint32_t)s->stack;
+    if (const char *cap = std::getenv("B200RT_DEBUG_STACK_CAP")) s->d.dbg.stack_cap = (uint32_t)std::max(0, std::min(s->stack, std::atoi(cap)));
+#endif
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, std::string("scene setup: ") + cudaGetErrorString(e)); }
+    return B200RT_OK;
+}
+
+// Builds the acceleration structure for `desc` and makes the scene resident on device `dev`.
+int create_scene_on(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, int dev, SceneImpl **out) {
+    *out = nullptr;
+    SceneImpl *s = new SceneImpl();
+    s->device = dev;
+    DeviceGuard g(dev);
+    if (!g.ok) { delete s; return fail(B200RT_ECUDA, "cudaSetDevice failed"); }
+    const uint64_t n_prims = desc->n_spheres + desc->n_quads;
+    int builder = opts ? opts->builder : B200RT_BUILDER_AUTO;
+    // AUTO: SAH on the host for small scenes (sub-millisecond, slightly better trees: +5 % on the
+    // 4 k-sphere scene), Morton LBVH on the GPU from 64 k primitives up (2.2 M / 3.1 M primitives:
+    // tens of ms incl. the upload vs 0.8 / 1.0 s, with equal or better render rates)
+    if (builder == B200RT_BUILDER_AUTO) builder = n_prims >= 65536 ? B200RT_BUILDER_GPU_LBVH : B200RT_BUILDER_HOST_SAH;
+    bool built = false;
+    if (builder == B200RT_BUILDER_GPU_LBVH && n_prims >= 2) {
+        bool too_deep = false;
+        if (int rc = scene_build_gpu(desc, s, &too_deep)) { free_scene(s); return rc; }
+        if (too_deep) {   // pathological depth: start over with the depth-capped host builder
+            for (int i = 0; i < 6; ++i) { dev_free(s->allocs[i]); s->allocs[i] = nullptr; s->alloc_bytes[i] = 0; }
+        } else {
+            built = true;
+        }
+    }
+    if (!built) {
+        if (int rc = scene_build_host(desc, opts, s)) { free_scene(s); return rc; }
+    }
+    s->info.n_prims = n_prims;
+    s->info.n_spheres = desc->n_spheres; s->info.n_quads = desc->n_quads; s->info.n_materials = desc->n_materials;
+    s->info.stack_entries = (uint32_t)s->stack;
+    if (int rc = finish_scene_setup(s)) { free_scene(s); return rc; }
+    *out = s;
+    return B200RT_OK;
+}
+
+// A copy of the resident scene `src` on device `dev`: six device-to-device copies (NVLink between peers), no rebuild.
+// The copies are enqueued on dev's default stream; the caller synchronises `dev` before the first render.
+int replicate_scene_on(const SceneImpl *src, int dev, SceneImpl **out) {
+    *out = nullptr;
+    SceneImpl *s = new SceneImpl();
+    s->device = dev;
+    DeviceGuard g(dev);
+    if (!g.ok) { delete s; return fail(B200RT_ECUDA, "cudaSetDevice failed"); }
+    for (int i = 0; i < 6; ++i) {
+        if (!src->allocs[i]) continue;
+        cudaError_t e = dev_alloc_async(&s->allocs[i], src->alloc_bytes[i], 0);
+        if (e == cudaSuccess) e = cudaMemcpyPeerAsync(s->allocs[i], dev, src->allocs[i], src->device, src->alloc_bytes[i], 0);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            free_scene(s);
+            return fail(e == cudaErrorMemoryAllocation ? B200RT_ENOMEM : B200RT_ECUDA, std::string("scene copy to a peer device: ") + cudaGetErrorString(e));
+        }
+        s->alloc_bytes[i] = src->alloc_bytes[i];
+    }
+    s->d.nodes = static_cast<const float4 *>(s->allocs[0]);
+    s->d.spheres = static_cast<const double2 *>(s->allocs[1]);
+    s->d.sphere_meta = static_cast<const uint2 *>(s->allocs[2]);
+    s->d.quads = static_cast<const double2 *>(s->allocs[3]);
+    s->d.quad_meta = static_cast<const uint2 *>(s->allocs[4]);
+    s->d.materials = static_cast<const DeviceMaterial *>(s->allocs[5]);
+    if (reinterpret_cast<uintptr_t>(s->d.nodes) & 127) { free_scene(s); return fail(B200RT_ECUDA, "node array is not 128-byte aligned"); }
+    s->info = src->info;
+    s->stack = src->stack;
+    if (int rc = finish_scene_setup(s)) { free_scene(s); return rc; }
+    *out = s;
+    return B200RT_OK;
+}
+
+void collect_stats(SceneImpl *s, B200rtStats *st) {   // after the stream that rendered has been synchronised
+    unsigned long long c[3] = {0, 0, 0};
+    cudaMemcpy(c, s->d_counters, sizeof c, cudaMemcpyDeviceToHost);
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) != cudaSuccess) { cudaGetLastError(); ms = 0; }
+    st->kernel_ms = ms;
+    st->rays = c[0]; st->node_visits = c[1]; st->prim_tests = c[2];
+}
+
+// One frame on all devices of `m` into the caller's host buffer: sample split, exchange, scale, read back.
+int render_multi(MultiImpl *m, const B200rtCamera *cam, const B200rtRenderOpts *opts, float *out_rgb, B200rtStats *stats) {
+    std::lock_guard<std::mutex> lk(m->mu);
+    const double t0 = now_ms();
+    CameraParams C{};
+    if (int rc = fill_camera(cam, C)) return rc;
+    B200rtRenderOpts o{};
+    if (opts) o = *opts;
+    uint64_t count = 0;
+    if (int rc = sample_range_of(cam, o, &count)) return rc;
+    const int n = (int)m->dev.size();
+    const long long n_pixels = (long long)cam->image_w * cam->image_h;
+    const size_t floats = (size_t)n_pixels * 3;
+    if (floats > m->frame_floats) {
+        for (int d = 0; d < n; ++d) {
+            DeviceGuard g(m->dev[d]->device);
+            dev_free(m->frame[d]); m->frame[d] = nullptr;
+            if (d == 0) { dev_free(m->scratch); m->scratch = nullptr; }
+            m->frame_floats = 0;
+            CUDA_TRY(dev_alloc(&m->frame[d], floats * sizeof(float)));
+            if (d == 0 && !m->peers) CUDA_TRY(dev_alloc(&m->scratch, floats * sizeof(float)));
+        }
+        m->frame_floats = floats;
+    }
+    std::vector<B200rtStats> st(n);
+    for (int d = 0; d < n; ++d) {   // rank d of n: samples [count*d/n, count*(d+1)/n) of the requested range, as a SUM
+        DeviceGuard g(m->dev[d]->device);
+        B200rtRenderOpts od = o;
+        const uint64_t lo = count * (uint64_t)d / (uint64_t)n, hi = count * (uint64_t)(d + 1) / (uint64_t)n;
+        od.sample_offset = o.sample_offset + lo;
+        od.sample_count = hi - lo;
+        od.flags = (o.flags & B200RT_FLAG_COUNTERS) | B200RT_FLAG_SUM | B200RT_FLAG_EXACT_COUNT;
+        if (int rc = render_on_device(m->dev[d], cam, &od, m->frame[d], m->stream[d], &st[d], false)) return rc;
+        CUDA_TRY(cudaEventRecord(m->ev_render[d], m->stream[d]));
+    }
+    const float scale = (o.flags & B200RT_FLAG_SUM) || count == 0 ? 1.0f : (float)(1.0 / (double)count);
+    cudaEvent_t x0 = nullptr, x1 = nullptr;
+    {
+        DeviceGuard g(m->dev[0]->device);
+        CUDA_TRY(cudaEventCreate(&x0));
+        CUDA_TRY(cudaEventCreate(&x1));
+    }
+    struct EvGuard { cudaEvent_t &a, &b; ~EvGuard() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); } } evg{x0, x1};
+    unsigned long long xchg_launches = 0;
+    if (m->peers) {
+        // one launch per device over peer-mapped frames: device d sums ITS slice of every frame in device order,
+        // scales and writes the result into devices[0]'s frame (reduce-scatter + scale + gather in one pass)
+        PeerFrames in{};
+        for (int r = 0; r < n; ++r) in.p[r] = m->frame[r];
+        for (int d = 0; d < n; ++d) {
+            DeviceGuard g(m->dev[d]->device);
+            for (int r = 0; r < n; ++r)
+                if (r != d) CUDA_TRY(cudaStreamWaitEvent(m->stream[d], m->ev_render[r], 0));
+            if (d == 0) CUDA_TRY(cudaEventRecord(x0, m->stream[0]));
+            CUDA_TRY(launch_reduce_finalize_peers(in, n, d, n_pixels, scale, m->frame[0], nullptr, 0, m->stream[d]));
+            CUDA_TRY(cudaEventRecord(m->ev_xchg[d], m->stream[d]));
+            ++xchg_launches;
+        }
+        DeviceGuard g(m->dev[0]->device);
+        for (int d = 1; d < n; ++d) CUDA_TRY(cudaStreamWaitEvent(m->stream[0], m->ev_xchg[d], 0));
+        CUDA_TRY(cudaEventRecord(x1, m->stream[0]));
+    } else {
+        // no peer mapping: copy each frame to devices[0] and add there, in device order (the same sums, bit for bit)
+        DeviceGuard g(m->dev[0]->device);
+        CUDA_TRY(cudaEventRecord(x0, m->stream[0]));
+        for (int r = 1; r < n; ++r) {
+            CUDA_TRY(cudaStreamWaitEvent(m->stream[0], m->ev_render[r], 0));
+            CUDA_TRY(cudaMemcpyPeerAsync(m->scratch, m->dev[0]->device, m->frame[r], m->dev[r]->device, floats * sizeof(float), m->stream[0]));
+            CUDA_TRY(launch_add_frame(m->frame[0], m->scratch, (long long)floats, m->stream[0]));
+            ++xchg_launches;
+        }
+        CUDA_TRY(launch_finalize(m->frame[0], n_pixels, scale, nullptr, 0, m->stream[0]));
+        ++xchg_launches;
+        CUDA_TRY(cudaEventRecord(x1, m->stream[0]));
+    }
+    double d2h_ms = 0;
+    {
+        DeviceGuard g(m->dev[0]->device);
+        CUDA_TRY(cudaStreamSynchronize(m->stream[0]));
+        const double t1 = now_ms();
+        CUDA_TRY(staged_download(out_rgb, m->frame[0], floats * sizeof(float), m->stream[0]));
+        d2h_ms = now_ms() - t1;
+    }
+    B200rtStats total{};
+    total.n_devices = (uint32_t)n;
+    total.peer_exchange = m->peers ? 1u : 0u;
+    for (int d = 0; d < n; ++d) {
+        DeviceGuard g(m->dev[d]->device);
+        CUDA_TRY(cudaStreamSynchronize(m->stream[d]));   // also: nobody reads this device's frame any more
+        collect_stats(m->dev[d], &st[d]);
+        total.kernel_ms = std::max(total.kernel_ms, st[d].kernel_ms);
+        total.paths += st[d].paths; total.rays += st[d].rays;
+        total.node_visits += st[d].node_visits; total.prim_tests += st[d].prim_tests;
+        total.kernel_launches += st[d].kernel_launches;
+    }
+    {
+        DeviceGuard g(m->dev[0]->device);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, x0, x1) == cudaSuccess) total.exchange_ms = ms; else cudaGetLastError();
+    }
+    total.kernel_launches += xchg_launches;
+    total.d2h_ms = d2h_ms;
+    total.d2h_bytes = floats * sizeof(float);
+    total.replicate_ms = m->replicate_ms;
+    total.total_ms = now_ms() - t0;
+    if (stats) *stats = total;
     return B200RT_OK;
 }
 
@@ -487,6 +739,12 @@ int b200rt_camera_init(B200rtCamera *c) {
     return B200RT_OK;
 }
 
+int b200rt_trim(void) {
+    if (device_count_quiet() == 0) return B200RT_OK;
+    if (dev_pool_trim_all() != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, "cudaMemPoolTrimTo failed"); }
+    return B200RT_OK;
+}
+
 int b200rt_scene_create(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, void **scene_out) {
     if (!scene_out) return fail(B200RT_EINVAL, "scene_out is NULL");
     *scene_out = nullptr;
@@ -494,60 +752,155 @@ int b200rt_scene_create(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts
     if (device_count_quiet() == 0) return fail(B200RT_ENODEVICE, "no CUDA device: libb200rt has no CPU path");
     int dev = opts ? opts->device : -1;
     if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; } }
-    if (dev >= device_count_quiet()) return fail(B200RT_EINVAL, "device ordinal out of range");
-
-    SceneImpl *s = new SceneImpl();
-    s->device = dev;
-    DeviceGuard g(dev);
-    if (!g.ok) { delete s; return fail(B200RT_ECUDA, "cudaSetDevice failed"); }
-    const uint64_t n_prims = desc->n_spheres + desc->n_quads;
-    int builder = opts ? opts->builder : B200RT_BUILDER_AUTO;
-    // AUTO: SAH on the host for small scenes (sub-millisecond, slightly better trees: +5 % on the
-    // 4 k-sphere scene), Morton LBVH on the GPU from 64 k primitives up (2.2 M / 3.1 M primitives:
-    // 57 / 90 ms incl. the upload vs 0.8 / 1.0 s, with equal or better render rates)
-    if (builder == B200RT_BUILDER_AUTO) builder = n_prims >= 65536 ? B200RT_BUILDER_GPU_LBVH : B200RT_BUILDER_HOST_SAH;
-    bool built = false;
-    if (builder == B200RT_BUILDER_GPU_LBVH && n_prims >= 2) {
-        bool too_deep = false;
-        if (int rc = scene_build_gpu(desc, s, &too_deep)) { free_scene(s); return rc; }
-        if (too_deep) {   // pathological depth: start over with the depth-capped host builder
-            for (void *&p : s->allocs) { dev_free(p); p = nullptr; }
-        } else {
-            built = true;
-        }
-    }
-    if (!built) {
-        if (int rc = scene_build_host(desc, opts, s)) { free_scene(s); return rc; }
-    }
-    {
-        cudaError_t e = dev_alloc(&s->d_counters, 3 * sizeof(unsigned long long));
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
-        if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
-        if (e == cudaSuccess) e = cudaDeviceSynchronize();
-        if (e != cudaSuccess) { free_scene(s); return fail(B200RT_ECUDA, std::string("scene setup: ") + cudaGetErrorString(e)); }
-    }
-    s->info.n_prims = desc->n_spheres + desc->n_quads;
-    s->info.n_spheres = desc->n_spheres; s->info.n_quads = desc->n_quads; s->info.n_materials = desc->n_materials;
-    s->info.stack_entries = (uint32_t)s->stack;
+    if (dev >= device_count_quiet() || dev >= kMaxDevices) return fail(B200RT_EINVAL, "device ordinal out of range");
+    SceneImpl *s = nullptr;
+    if (int rc = create_scene_on(desc, opts, dev, &s)) return rc;
     *scene_out = s;
     return B200RT_OK;
 }
 
+int b200rt_scene_create_multi(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, const int32_t *devices, int32_t n_devices,
+                              void **scene_out) {
+    if (!scene_out) return fail(B200RT_EINVAL, "scene_out is NULL");
+    *scene_out = nullptr;
+    if (int rc = validate_desc(desc)) return rc;
+    const int have = device_count_quiet();
+    if (have == 0) return fail(B200RT_ENODEVICE, "no CUDA device: libb200rt has no CPU path");
+    if (n_devices < 1 || n_devices > kMaxPeers) return fail(B200RT_EINVAL, "device count must be 1 .. 16");
+    std::vector<int> devs(n_devices);
+    for (int i = 0; i < n_devices; ++i) {
+        devs[i] = devices ? devices[i] : i;
+        if (devs[i] < 0 || devs[i] >= have || devs[i] >= kMaxDevices) return fail(B200RT_EINVAL, "device ordinal out of range");
+        for (int j = 0; j < i; ++j)
+            if (devs[j] == devs[i]) return fail(B200RT_EINVAL, "a device is listed twice");
+    }
+    if (n_devices == 1) {
+        SceneImpl *s = nullptr;
+        if (int rc = create_scene_on(desc, opts, devs[0], &s)) return rc;
+        *scene_out = s;
+        return B200RT_OK;
+    }
+    MultiImpl *m = new MultiImpl();
+    m->dev.assign(n_devices, nullptr);
+    m->stream.assign(n_devices, nullptr);
+    m->ev_render.assign(n_devices, nullptr);
+    m->ev_xchg.assign(n_devices, nullptr);
+    m->frame.assign(n_devices, nullptr);
+    if (int rc = create_scene_on(desc, opts, devs[0], &m->dev[0])) { free_multi(m); return rc; }
+    const double t0 = now_ms();
+    // Peer mapping: every device must be able to dereference every other device's pool memory for the fused
+    // exchange; cudaMemcpyPeerAsync (the scene copies) works either way but goes over NVLink only between peers.
+    bool all_peers = true;
+    for (int i = 0; i < n_devices; ++i) {
+        DeviceGuard g(devs[i]);
+        for (int j = 0; j < n_devices; ++j) {
+            if (i == j) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) != cudaSuccess) { cudaGetLastError(); can = 0; }
+            if (!can) { all_peers = false; continue; }
+            const cudaError_t e = cudaDeviceEnablePeerAccess(devs[j], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) all_peers = false;
+            cudaGetLastError();
+        }
+    }
+    if (all_peers)
+        for (int i = 0; i < n_devices; ++i)
+            if (dev_pool_allow_peers(devs[i], devs.data(), n_devices) != cudaSuccess) { cudaGetLastError(); all_peers = false; }
+    m->peers = all_peers;
+    for (int i = 1; i < n_devices; ++i)   // all copies are in flight together, one per destination device
+        if (int rc = replicate_scene_on(m->dev[0], devs[i], &m->dev[i])) { free_multi(m); return rc; }
+    for (int i = 0; i < n_devices; ++i) {
+        DeviceGuard g(devs[i]);
+        cudaError_t e = cudaStreamCreateWithFlags(&m->stream[i], cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_render[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&m->ev_xchg[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();   // this device's copy of the scene has landed
+        if (e != cudaSuccess) { cudaGetLastError(); free_multi(m); return fail(B200RT_ECUDA, std::string("multi-device setup: ") + cudaGetErrorString(e)); }
+    }
+    m->replicate_ms = now_ms() - t0;
+    *scene_out = m;
+    return B200RT_OK;
+}
+
 int b200rt_scene_info(void *scene, B200rtSceneInfo *info) {
-    SceneImpl *s = as_scene(scene);
+    SceneImpl *s = root_scene(scene);
     if (!s || !info) return fail(B200RT_EINVAL, "bad scene handle");
     *info = s->info;
     return B200RT_OK;
 }
 
-void b200rt_scene_destroy(void *scene) { free_scene(as_scene(scene)); }
+void b200rt_scene_destroy(void *scene) {
+    if (MultiImpl *m = as_multi(scene)) free_multi(m);
+    else free_scene(as_scene(scene));
+}
+
+int b200rt_debug_bounds(void *scene, uint64_t *out) {
+#ifdef B200RT_DEBUG_BOUNDS
+    if (!out) return fail(B200RT_EINVAL, "output pointer is NULL");
+    for (int k = 0; k < 4; ++k) out[k] = 0;
+    std::vector<SceneImpl *> all;
+    if (MultiImpl *m = as_multi(scene)) all = m->dev;
+    else if (SceneImpl *s = as_scene(scene)) all.push_back(s);
+    else return fail(B200RT_EINVAL, "bad scene handle");
+    for (SceneImpl *s : all) {
+        DeviceGuard g(s->device);
+        unsigned long long v[4];
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpy(v, s->d_viol, sizeof v, cudaMemcpyDeviceToHost));
+        for (int k = 0; k < 4; ++k) out[k] += v[k];
+    }
+    return B200RT_OK;
+#else
+    (void)scene; (void)out;
+    return fail(B200RT_EINVAL, "this libb200rt was built without -DB200RT_DEBUG_BOUNDS");
+#endif
+}
+
+int b200rt_debug_philox(const uint32_t *counters_keys, int64_t n, uint32_t *out, int device) {
+    if (n < 0 || (n && (!counters_keys || !out))) return fail(B200RT_EINVAL, "bad debug_philox buffers");
+    if (device_count_quiet() == 0) return fail(B200RT_ENODEVICE, "no CUDA device: libb200rt has no CPU path");
+    if (n == 0) return B200RT_OK;
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; } }
+    DeviceGuard g(device);
+    uint32_t *d_in = nullptr, *d_out = nullptr;
+    cudaError_t e = dev_alloc(&d_in, (size_t)n * 6 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = dev_alloc(&d_out, (size_t)n * 4 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, counters_keys, (size_t)n * 6 * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_debug_philox(d_in, n, d_out, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(out, d_out, (size_t)n * 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost);
+    cudaStreamSynchronize(0);
+    dev_free(d_in); dev_free(d_out);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, std::string("debug_philox: ") + cudaGetErrorString(e)); }
+    return B200RT_OK;
+}
+
+int b200rt_debug_samplers(const uint32_t *rnd_pairs, int64_t n, double *sphere_out, double *disk_out, int device) {
+    if (n < 0 || (n && (!rnd_pairs || !sphere_out || !disk_out))) return fail(B200RT_EINVAL, "bad debug_samplers buffers");
+    if (device_count_quiet() == 0) return fail(B200RT_ENODEVICE, "no CUDA device: libb200rt has no CPU path");
+    if (n == 0) return B200RT_OK;
+    if (device < 0) { if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); device = 0; } }
+    DeviceGuard g(device);
+    uint32_t *d_in = nullptr;
+    double *d_s = nullptr, *d_d = nullptr;
+    cudaError_t e = dev_alloc(&d_in, (size_t)n * 2 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = dev_alloc(&d_s, (size_t)n * 3 * sizeof(double));
+    if (e == cudaSuccess) e = dev_alloc(&d_d, (size_t)n * 2 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(d_in, rnd_pairs, (size_t)n * 2 * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_debug_samplers(d_in, n, d_s, d_d, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(sphere_out, d_s, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(disk_out, d_d, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaStreamSynchronize(0);
+    dev_free(d_in); dev_free(d_s); dev_free(d_d);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, std::string("debug_samplers: ") + cudaGetErrorString(e)); }
+    return B200RT_OK;
+}
 
 int b200rt_raycast(void *scene, const double *rays, int64_t n, double tmin, double tmax, int32_t *prim_out, double *t_out) {
-    SceneImpl *s = as_scene(scene);
+    SceneImpl *s = root_scene(scene);
     if (!s) return fail(B200RT_EINVAL, "bad scene handle");
     if (n < 0 || (n && (!rays || !prim_out || !t_out))) return fail(B200RT_EINVAL, "bad ray buffers");
     if (n == 0) return B200RT_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
     DeviceGuard g(s->device);
     if ((size_t)n > s->ray_capacity) {
         if (s->d_rays) { dev_free(s->d_rays); dev_free(s->d_prim); dev_free(s->d_t); s->d_rays = nullptr; s->d_prim = nullptr; s->d_t = nullptr; }
@@ -591,10 +944,11 @@ int b200rt_debug_camera_rays(const B200rtCamera *cam, const uint32_t *pixels_xy,
 int b200rt_debug_shade(void *scene, const double *rays, const uint32_t *rnd, int64_t n, double tmin, double tmax,
                        B200rtShadeRecord *records_out) {
     static_assert(sizeof(B200rtShadeRecord) == 88, "record layout is shared with kernels.cu");
-    SceneImpl *s = as_scene(scene);
+    SceneImpl *s = root_scene(scene);
     if (!s) return fail(B200RT_EINVAL, "bad scene handle");
     if (n < 0 || (n && (!rays || !rnd || !records_out))) return fail(B200RT_EINVAL, "bad debug_shade buffers");
     if (n == 0) return B200RT_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
     DeviceGuard g(s->device);
     double *d_rays = nullptr;
     uint32_t *d_rnd = nullptr;
@@ -612,19 +966,55 @@ int b200rt_debug_shade(void *scene, const double *rays, const uint32_t *rnd, int
     return B200RT_OK;
 }
 
+int b200rt_debug_lane_accounting(void *scene, const B200rtCamera *cam, const B200rtRenderOpts *opts, uint64_t *counters_out) {
+    SceneImpl *s = root_scene(scene);
+    if (!s) return fail(B200RT_EINVAL, "bad scene handle");
+    if (!cam || !counters_out) return fail(B200RT_EINVAL, "camera or output pointer is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    DeviceGuard g(s->device);
+    RenderParams P{};
+    if (int rc = fill_camera(cam, P.cam)) return rc;
+    B200rtRenderOpts o{};
+    if (opts) o = *opts;
+    uint64_t count = 0;
+    if (int rc = sample_range_of(cam, o, &count)) return rc;
+    float *d_frame = nullptr;
+    unsigned long long *d_acc = nullptr;
+    CUDA_TRY(dev_alloc(&d_frame, (size_t)cam->image_w * cam->image_h * 3 * sizeof(float)));
+    cudaError_t e = dev_alloc(&d_acc, 16 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_acc, 0, 16 * sizeof(unsigned long long), 0);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_counters, 0, 3 * sizeof(unsigned long long), 0);
+    P.scene = s->d; P.seed = o.seed; P.sample_begin = (uint32_t)o.sample_offset; P.sample_count = (uint32_t)count;
+    P.out = d_frame; P.flags = 0; P.scale = 1.0f; P.counters = s->d_counters;
+    if (e == cudaSuccess) e = launch_path_lanes(s->stack, P, d_acc, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(counters_out, d_acc, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    cudaStreamSynchronize(0);
+    dev_free(d_frame); dev_free(d_acc);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, std::string("lane accounting: ") + cudaGetErrorString(e)); }
+    return B200RT_OK;
+}
+
 int b200rt_render_device(void *scene, const B200rtCamera *cam, const B200rtRenderOpts *opts, float *out_rgb_device,
                          void *stream, B200rtStats *stats) {
+    if (as_multi(scene)) return fail(B200RT_EINVAL, "b200rt_render_device takes a single-device scene (a multi-device scene renders through b200rt_render)");
     SceneImpl *s = as_scene(scene);
     if (!s) return fail(B200RT_EINVAL, "bad scene handle");
     if (!out_rgb_device) return fail(B200RT_EINVAL, "output pointer is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
     DeviceGuard g(s->device);
     return render_on_device(s, cam, opts, out_rgb_device, static_cast<cudaStream_t>(stream), stats, stats != nullptr);
 }
 
 int b200rt_render(void *scene, const B200rtCamera *cam, const B200rtRenderOpts *opts, float *out_rgb, B200rtStats *stats) {
+    if (!cam || !out_rgb) return fail(B200RT_EINVAL, "camera or output pointer is NULL");
+    if (MultiImpl *m = as_multi(scene)) return render_multi(m, cam, opts, out_rgb, stats);
     SceneImpl *s = as_scene(scene);
     if (!s) return fail(B200RT_EINVAL, "bad scene handle");
-    if (!cam || !out_rgb) return fail(B200RT_EINVAL, "camera or output pointer is NULL");
+    {
+        CameraParams C{};
+        if (int rc = fill_camera(cam, C)) return rc;   // range-checks the dimensions BEFORE anything is sized by them
+    }
+    std::lock_guard<std::mutex> lk(s->mu);
     DeviceGuard g(s->device);
     const double t0 = now_ms();
     const size_t floats = (size_t)cam->image_w * cam->image_h * 3;
@@ -639,7 +1029,7 @@ int b200rt_render(void *scene, const B200rtCamera *cam, const B200rtRenderOpts *
     B200rtStats local{};
     if (int rc = render_on_device(s, cam, &o, s->d_frame, 0, &local, true)) return rc;
     const double t1 = now_ms();
-    CUDA_TRY(cudaMemcpy(out_rgb, s->d_frame, floats * sizeof(float), cudaMemcpyDeviceToHost));
+    CUDA_TRY(staged_download(out_rgb, s->d_frame, floats * sizeof(float), 0));
     const double t2 = now_ms();
     local.d2h_ms = t2 - t1;
     local.d2h_bytes = floats * sizeof(float);
@@ -648,23 +1038,37 @@ int b200rt_render(void *scene, const B200rtCamera *cam, const B200rtRenderOpts *
     return B200RT_OK;
 }
 
-int b200rt_render_scene(const B200rtSceneDesc *desc, const B200rtCamera *cam, const B200rtRenderOpts *opts,
-                        const B200rtBuildOpts *bopts, float *out_rgb, B200rtStats *stats, B200rtSceneInfo *info) {
+int b200rt_render_scene_multi(const B200rtSceneDesc *desc, const B200rtCamera *cam, const B200rtRenderOpts *opts,
+                              const B200rtBuildOpts *bopts, const int32_t *devices, int32_t n_devices, float *out_rgb,
+                              B200rtStats *stats, B200rtSceneInfo *info) {
     const double t0 = now_ms();
+    if (!cam || !out_rgb) return fail(B200RT_EINVAL, "camera or output pointer is NULL");
+    {
+        CameraParams C{};
+        if (int rc = fill_camera(cam, C)) return rc;   // reject a bad camera before paying for the build
+    }
     void *scene = nullptr;
-    if (int rc = b200rt_scene_create(desc, bopts, &scene)) return rc;
+    if (int rc = b200rt_scene_create_multi(desc, bopts, devices, n_devices, &scene)) return rc;
     B200rtStats local{};
     int rc = b200rt_render(scene, cam, opts, out_rgb, &local);
-    SceneImpl *s = as_scene(scene);
     if (!rc) {
+        const SceneImpl *s = root_scene(scene);
         local.h2d_ms = s->info.upload_ms;
         local.h2d_bytes = s->info.device_bytes;
+        local.build_ms = s->info.build_ms + s->info.upload_ms;
         if (info) *info = s->info;
     }
     b200rt_scene_destroy(scene);
     local.total_ms = now_ms() - t0;
     if (!rc && stats) *stats = local;
     return rc;
+}
+
+int b200rt_render_scene(const B200rtSceneDesc *desc, const B200rtCamera *cam, const B200rtRenderOpts *opts,
+                        const B200rtBuildOpts *bopts, float *out_rgb, B200rtStats *stats, B200rtSceneInfo *info) {
+    int32_t dev = bopts ? bopts->device : -1;
+    if (dev < 0) { int cur = 0; if (cudaGetDevice(&cur) != cudaSuccess) { cudaGetLastError(); cur = 0; } dev = cur; }
+    return b200rt_render_scene_multi(desc, cam, opts, bopts, &dev, 1, out_rgb, stats, info);
 }
 
 int b200rt_tonemap_device(const float *hdr_device, int64_t n_pixels, int32_t *out_device, int clamp, int device, void *stream) {

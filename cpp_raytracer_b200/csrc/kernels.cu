@@ -6,7 +6,6 @@
 //   path_megakernel       one thread per pixel, all of that pixel's samples, with path regeneration:
 //                         a lane whose path ended starts its next sample right away
 //                         [Camera::render<T> + ray_color, reference camera.h:205-297]
-//   path_megakernel_voted experiment kept for A/B (variant 2): warp-voted step scheduling
 //   tonemap_kernel        Reinhard + gamma 2 + int(255.999999 v)   [RGB::as_string, rgb.h:90-113]
 #include "kernels.h"
 #include "shade.cuh"
@@ -59,6 +58,26 @@ __global__ void debug_camera_kernel(const __grid_constant__ CameraParams C, cons
     o[0] = r.ox; o[1] = r.oy; o[2] = r.oz; o[3] = r.dx; o[4] = r.dy; o[5] = r.dz;
 }
 
+// Test hooks (b200rt_debug_philox / b200rt_debug_samplers): the generator and the direction samplers exactly as the
+// path kernels call them, on caller-supplied inputs.
+__global__ void debug_philox_kernel(const uint32_t *__restrict__ in, long long n, uint32_t *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Philox4 r = philox4x32_10(in[i * 6 + 0], in[i * 6 + 1], in[i * 6 + 2], in[i * 6 + 3], in[i * 6 + 4], in[i * 6 + 5]);
+    out[i * 4 + 0] = r.x; out[i * 4 + 1] = r.y; out[i * 4 + 2] = r.z; out[i * 4 + 3] = r.w;
+}
+__global__ void debug_samplers_kernel(const uint32_t *__restrict__ rnd, long long n, double *__restrict__ sphere_out,
+                                      double *__restrict__ disk_out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x, y, z;
+    sample_unit_sphere(u01(rnd[i * 2 + 0]), u01(rnd[i * 2 + 1]), x, y, z);
+    sphere_out[i * 3 + 0] = x; sphere_out[i * 3 + 1] = y; sphere_out[i * 3 + 2] = z;
+    double ax, ay;
+    sample_unit_disk(u01(rnd[i * 2 + 0]), u01(rnd[i * 2 + 1]), ax, ay);
+    disk_out[i * 2 + 0] = ax; disk_out[i * 2 + 1] = ay;
+}
+
 template <int STACK>
 __global__ void __launch_bounds__(128) debug_shade_kernel(DeviceScene S, const double *__restrict__ rays,
                                                           const uint32_t *__restrict__ rnd, long long n, double tmin, double tmax,
@@ -109,7 +128,7 @@ __device__ __forceinline__ void write_pixel_and_counters(const RenderParams &P, 
                                                          float sum_b, uint32_t lane_rays, bool count,
                                                          const TraversalCounters &ctr) {
     unsigned long long rays = lane_rays;
-    if (m.valid) {
+    if (m.valid && B200RT_CHECK(P.scene, m.pixel < P.cam.w * P.cam.h, 3)) {
         float *o = P.out + (size_t)m.pixel * 3;
         const float k = P.scale;
         if (P.flags & kRenderAccumulate) { o[0] += sum_r * k; o[1] += sum_g * k; o[2] += sum_b * k; }
@@ -169,54 +188,6 @@ __device__ __forceinline__ bool shade_and_advance(const RenderParams &P, const P
 }
 
 // ------------------------------------------------------------------------------------------
-// path_megakernel_voted (variant 2, EXPERIMENT, not the default).  One loop, one step per lane per
-// iteration; a lane that finished its traversal PARKS until at least B200RT_SHADE_AT lanes of the warp
-// are parked (or nobody traverses any more), then the parked lanes shade + start their next ray
-// together while the others keep traversing.  Against the default kernel this removes the tail of
-// every traversal round (where one or two slow lanes hold the warp) at the price of two ballots per
-// iteration and a shade step that runs below full width.  (An earlier form voted between node, leaf
-// and shade steps by majority: 12.7 -> 14.4 active threads per instruction, +16 % instructions, no gain.)
-#ifndef B200RT_SHADE_AT
-#define B200RT_SHADE_AT 24
-#endif
-template <int STACK, bool COUNT>
-__global__ void __launch_bounds__(kPathBlock, kPathMinBlocks) path_megakernel_voted(const __grid_constant__ RenderParams P) {
-    const CameraParams &C = P.cam;
-    const PixelMap m = map_pixel(C);
-    LaneState L;
-    TraversalCounters ctr;
-    Trav T;
-    uint2 stack[STACK];
-    T.cur = kTravDone;
-    bool done = !(m.valid && C.max_depth > 0 && P.sample_count > 0);
-
-    while (true) {
-        const bool parked = !done && trav_done(T);
-        const bool tracing = !done && !trav_done(T);
-        const unsigned m_parked = __ballot_sync(0xffffffffu, parked);
-        const unsigned m_tracing = __ballot_sync(0xffffffffu, tracing);
-        if (!(m_parked | m_tracing)) break;
-        if (m_parked && (m_tracing == 0u || __popc(m_parked) >= B200RT_SHADE_AT)) {
-            if (parked) {
-                if (shade_and_advance(P, m, T.best, L))
-                    trav_init(T, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001,   // camera.h:217
-                              __longlong_as_double(0x7ff0000000000000LL));
-                else
-                    done = true;
-            }
-        } else if (tracing) {
-            if (trav_at_node(T)) {
-                if (COUNT) ctr.nodes++;
-                trav_node_step(P.scene, T, stack);
-            } else {
-                const uint32_t c = trav_leaf_step(P.scene, T, stack);
-                if (COUNT) ctr.prims += c;
-            }
-        }
-    }
-    write_pixel_and_counters(P, m, L.sum_r, L.sum_g, L.sum_b, L.rays, COUNT, ctr);
-}
-
 // path_megakernel (variant 0, default): every lane runs traverse-then-shade in a loop and starts
 // its next sample as soon as a path ends.  64 registers (16 blocks = 32 warps per SM) measured
 // fastest on B200: 8/12/16/20/24 blocks per SM gave 2707/3171/3263/2630/2307 Mpaths/s on C2.
@@ -235,6 +206,72 @@ __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel(const __grid
         }
     }
     write_pixel_and_counters(P, m, L.sum_r, L.sum_g, L.sum_b, L.rays, COUNT, ctr);
+}
+
+// ------------------------------------------------------------------------------------------
+// path_lanes_kernel: MEASUREMENT ONLY (b200rt_debug_lane_accounting).  The default kernel's schedule -- per
+// round every lane shades / regenerates, then the warp runs one traversal step per lane per iteration until
+// its slowest lane is done -- replayed warp-synchronously so that each warp can count, per executed step,
+// how many of its 32 lanes took part and what the others were doing:
+//   acc[0] shade executions           acc[1] lanes taking part
+//   acc[2] node-step executions       acc[3] lanes at a node     acc[4] idle: at a leaf   acc[5] idle: traversal done,
+//                                                                waiting for the round    acc[6] idle: pixel out of samples
+//   acc[7] leaf-step executions       acc[8] lanes at a leaf     acc[9] idle: at a node   acc[10] idle: done   acc[11] idle: finished
+//   acc[12] primitive-test executions (a leaf step loops over its primitives)            acc[13] lanes taking part
+//   acc[14] warps   acc[15] lane-rounds (shade calls that started a ray)
+// Same Philox keys and the same arithmetic as path_megakernel, so it also writes the same image.
+template <int STACK>
+__global__ void __launch_bounds__(kPathBlock) path_lanes_kernel(const __grid_constant__ RenderParams P, unsigned long long *__restrict__ acc) {
+    const CameraParams &C = P.cam;
+    const PixelMap m = map_pixel(C);
+    LaneState L;
+    Trav T;
+    uint2 stack[STACK];
+    T.cur = kTravDone;
+    T.best.t = 0.0; T.best.ref = kNoHit;
+    bool finished = !(m.valid && C.max_depth > 0 && P.sample_count > 0);
+    unsigned long long a[16] = {};
+    const unsigned full = 0xffffffffu;
+    while (true) {
+        const unsigned ms = __ballot_sync(full, !finished);
+        if (!ms) break;
+        a[0]++; a[1] += __popc(ms);
+        if (!finished) {
+            if (shade_and_advance(P, m, T.best, L)) {
+                a[15]++;
+                trav_init(T, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001, __longlong_as_double(0x7ff0000000000000LL));
+            } else {
+                finished = true;
+                T.cur = kTravDone;
+            }
+        }
+        while (true) {
+            const bool node = !finished && trav_at_node(T), leaf = !finished && trav_at_leaf(T);
+            const unsigned mn = __ballot_sync(full, node), ml = __ballot_sync(full, leaf), mf = __ballot_sync(full, finished);
+            if (!(mn | ml)) break;
+            const unsigned md = ~(mn | ml | mf);
+            if (mn) { a[2]++; a[3] += __popc(mn); a[4] += __popc(ml); a[5] += __popc(md); a[6] += __popc(mf); }
+            if (ml) {
+                a[7]++; a[8] += __popc(ml); a[9] += __popc(mn); a[10] += __popc(md); a[11] += __popc(mf);
+                const uint32_t cnt = leaf ? ((T.cur >> 26) & 0xFu) : 0u;
+                for (uint32_t i = 0; i < 8; ++i) {
+                    const unsigned mi = __ballot_sync(full, cnt > i);
+                    if (!mi) break;
+                    a[12]++; a[13] += __popc(mi);
+                }
+            }
+            if (node) trav_node_step(P.scene, T, stack);
+            else if (leaf) trav_leaf_step(P.scene, T, stack);
+        }
+    }
+    TraversalCounters ctr;
+    write_pixel_and_counters(P, m, L.sum_r, L.sum_g, L.sum_b, L.rays, false, ctr);
+    a[14] = 1;
+    unsigned long long rounds = a[15];
+    for (int off = 16; off; off >>= 1) rounds += __shfl_down_sync(full, rounds, off);
+    a[15] = rounds;
+    if ((threadIdx.x & 31) == 0)
+        for (int i = 0; i < 16; ++i) atomicAdd(&acc[i], a[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -370,6 +407,17 @@ cudaError_t launch_debug_camera(const CameraParams &C, const uint32_t *pixels, c
     return cudaGetLastError();
 }
 
+cudaError_t launch_debug_philox(const uint32_t *in, long long n, uint32_t *out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    debug_philox_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(in, n, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_debug_samplers(const uint32_t *rnd, long long n, double *sphere_out, double *disk_out, cudaStream_t st) {
+    if (n == 0) return cudaSuccess;
+    debug_samplers_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(rnd, n, sphere_out, disk_out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_debug_shade(int stack, const DeviceScene &S, const double *rays, const uint32_t *rnd, long long n, double tmin,
                                double tmax, void *records, cudaStream_t st) {
     if (n == 0) return cudaSuccess;
@@ -382,26 +430,30 @@ cudaError_t launch_debug_shade(int stack, const DeviceScene &S, const double *ra
 }
 
 template <int STACK>
-static cudaError_t launch_path_t(const RenderParams &P, bool count, bool voted, bool shallow, cudaStream_t st) {
+static cudaError_t launch_path_t(const RenderParams &P, bool count, bool shallow, cudaStream_t st) {
     const uint32_t tiles = ((P.cam.w + 7u) >> 3) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
     if (tiles == 0) return cudaSuccess;
-    if (!voted) {
-        if (STACK == 32 && shallow) {   // trees of depth <= 3 (a handful of nodes): while-while loop structure
-            if (count) path_megakernel<32, true, true><<<tiles, kPathBlock, 0, st>>>(P);
-            else path_megakernel<32, false, true><<<tiles, kPathBlock, 0, st>>>(P);
-        } else if (count) path_megakernel<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
-        else path_megakernel<STACK, false><<<tiles, kPathBlock, 0, st>>>(P);
-    } else {
-        if (count) path_megakernel_voted<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
-        else path_megakernel_voted<STACK, false><<<tiles, kPathBlock, 0, st>>>(P);
-    }
+    if (STACK == 32 && shallow) {   // trees of depth <= 3 (a handful of nodes): while-while loop structure
+        if (count) path_megakernel<32, true, true><<<tiles, kPathBlock, 0, st>>>(P);
+        else path_megakernel<32, false, true><<<tiles, kPathBlock, 0, st>>>(P);
+    } else if (count) path_megakernel<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
+    else path_megakernel<STACK, false><<<tiles, kPathBlock, 0, st>>>(P);
     return cudaGetLastError();
 }
 
-cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool voted, bool shallow, cudaStream_t st) {
-    if (stack <= 32) return launch_path_t<32>(P, count, voted, shallow, st);
-    if (stack <= 64) return launch_path_t<64>(P, count, voted, false, st);
-    return launch_path_t<128>(P, count, voted, false, st);
+cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool shallow, cudaStream_t st) {
+    if (stack <= 32) return launch_path_t<32>(P, count, shallow, st);
+    if (stack <= 64) return launch_path_t<64>(P, count, false, st);
+    return launch_path_t<128>(P, count, false, st);
+}
+
+cudaError_t launch_path_lanes(int stack, const RenderParams &P, unsigned long long *acc, cudaStream_t st) {
+    const uint32_t tiles = ((P.cam.w + 7u) >> 3) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
+    if (tiles == 0) return cudaSuccess;
+    if (stack <= 32) path_lanes_kernel<32><<<tiles, kPathBlock, 0, st>>>(P, acc);
+    else if (stack <= 64) path_lanes_kernel<64><<<tiles, kPathBlock, 0, st>>>(P, acc);
+    else path_lanes_kernel<128><<<tiles, kPathBlock, 0, st>>>(P, acc);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_tonemap(const float *hdr, long long n_pixels, int32_t *out, int clamp, cudaStream_t st) {
@@ -413,6 +465,16 @@ cudaError_t launch_tonemap(const float *hdr, long long n_pixels, int32_t *out, i
 cudaError_t launch_finalize(float *frame, long long n_pixels, float scale, int32_t *ldr, int clamp, cudaStream_t st) {
     if (n_pixels == 0) return cudaSuccess;
     finalize_kernel<<<(unsigned)((n_pixels + 255) / 256), 256, 0, st>>>(frame, n_pixels, scale, ldr, clamp);
+    return cudaGetLastError();
+}
+
+__global__ void add_frame_kernel(float *__restrict__ frame, const float *__restrict__ other, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) frame[i] += other[i];
+}
+cudaError_t launch_add_frame(float *frame, const float *other, long long n_floats, cudaStream_t st) {
+    if (n_floats == 0) return cudaSuccess;
+    add_frame_kernel<<<(unsigned)((n_floats + 255) / 256), 256, 0, st>>>(frame, other, n_floats);
     return cudaGetLastError();
 }
 

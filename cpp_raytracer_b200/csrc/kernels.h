@@ -64,11 +64,15 @@ cudaError_t run_wavefront(int stack, const RenderParams &P, const WavefrontPool 
 cudaError_t launch_raycast(int stack, const DeviceScene &S, const double *rays, long long n, double tmin, double tmax,
                            int32_t *prim, double *t, cudaStream_t st);
 // shallow: the tree has depth <= 3 -> while-while traversal loop (see closest_hit)
-cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool voted, bool shallow, cudaStream_t st);
+cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool shallow, cudaStream_t st);
+// measurement only: 16 lane-accounting counters (see path_lanes_kernel)
+cudaError_t launch_path_lanes(int stack, const RenderParams &P, unsigned long long *acc, cudaStream_t st);
 cudaError_t launch_finalize(float *frame, long long n_pixels, float scale, int32_t *ldr, int clamp, cudaStream_t st);
 cudaError_t launch_tonemap(const float *hdr, long long n_pixels, int32_t *out, int clamp, cudaStream_t st);
 cudaError_t launch_debug_camera(const CameraParams &C, const uint32_t *pixels, const uint32_t *rnd, long long n, double *rays_out,
                                 cudaStream_t st);
+cudaError_t launch_debug_philox(const uint32_t *in, long long n, uint32_t *out, cudaStream_t st);
+cudaError_t launch_debug_samplers(const uint32_t *rnd, long long n, double *sphere_out, double *disk_out, cudaStream_t st);
 // records: n x 88-byte ShadeRecord (kernels.cu)
 cudaError_t launch_debug_shade(int stack, const DeviceScene &S, const double *rays, const uint32_t *rnd, long long n, double tmin,
                                double tmax, void *records, cudaStream_t st);
@@ -77,6 +81,8 @@ cudaError_t launch_debug_shade(int stack, const DeviceScene &S, const double *ra
 constexpr int kMaxPeers = 16;
 struct PeerFrames { const float *p[kMaxPeers]; };
 void peer_slice(long long n_pixels, int n_peers, int rank, long long *lo, long long *hi);
+// frame += other (multi-GPU exchange without peer mapping: the root adds the copied per-device frames in order)
+cudaError_t launch_add_frame(float *frame, const float *other, long long n_floats, cudaStream_t st);
 cudaError_t launch_reduce_finalize_peers(const PeerFrames &in, int n_peers, int rank, long long n_pixels, float scale,
                                          float *root_hdr, int32_t *root_ldr, int clamp, cudaStream_t st);
 

@@ -25,6 +25,7 @@
 
 #include "../../include/b200rt.h"
 #include "bvh_builder.h"
+#include "devmem.h"
 #include "kernels.h"
 
 namespace b200rt {
@@ -296,7 +297,7 @@ __global__ void reorder_prims(const B200rtSphere *sph, uint32_t n_sph, const B20
 template <typename T>
 cudaError_t tmp_alloc(std::vector<void *> &owned, T **p, size_t count) {
     void *q = nullptr;
-    cudaError_t e = cudaMallocAsync(&q, (count ? count : 1) * sizeof(T), 0);
+    cudaError_t e = dev_alloc_async(&q, (count ? count : 1) * sizeof(T), 0);
     if (e != cudaSuccess) return e;
     owned.push_back(q);
     *p = static_cast<T *>(q);
@@ -313,10 +314,14 @@ cudaError_t build_lbvh_device(const B200rtSphere *d_sph, uint32_t n_sph, const B
                               double2 *out_sph, uint2 *out_sph_meta, double2 *out_quads, uint2 *out_quad_meta,
                               float4 **nodes_out, uint32_t *n_nodes_out, uint32_t *depth_out) {
     const uint32_t n = n_sph + n_quad;
-    if (n < 2) return cudaErrorInvalidValue;
+    // Encoding limits: a leaf reference holds a 26-bit index into its per-type array (bvh_builder.h), and the radix
+    // tree's index arithmetic ((n - 1) + ~child, lmax * d) must stay inside int.  The host builder rejects the same
+    // scenes (bvh_builder.cpp); api.cu checks before calling, this is the backstop.
+    if (n < 2 || n_sph > kLeafIndexMask || n_quad > kLeafIndexMask || n > (1u << 29)) return cudaErrorInvalidValue;
     std::vector<void *> owned;
-    auto cleanup = [&]() { for (void *p : owned) cudaFreeAsync(p, 0); };
-    auto fail = [&](cudaError_t e) { cleanup(); return e; };
+    Node4 *nodes4 = nullptr;
+    auto cleanup = [&]() { for (void *p : owned) dev_free(p); };
+    auto fail = [&](cudaError_t e) { cleanup(); dev_free(nodes4); return e; };
     const int B = 256;
     const unsigned gn = (n + B - 1) / B;
 #define LB(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) return fail(e_); } while (0)
@@ -366,8 +371,7 @@ cudaError_t build_lbvh_device(const B200rtSphere *d_sph, uint32_t n_sph, const B
     }
     reorder_prims<<<gn, B>>>(d_sph, n_sph, d_quads, vals, quad_rank, n, out_sph, out_sph_meta, out_quads, out_quad_meta);
     // breadth-first collapse to 4-wide nodes (at most n - 1 of them)
-    Node4 *nodes4 = nullptr;
-    LB(cudaMallocAsync((void **)&nodes4, (size_t)(n - 1) * sizeof(Node4), 0));
+    LB(dev_alloc_async(&nodes4, (size_t)(n - 1) * sizeof(Node4), 0));
     CollapseTask *qa, *qb;
     uint32_t *counters;   // [0] next queue size, [1] nodes emitted
     LB(tmp_alloc(owned, &qa, n)); LB(tmp_alloc(owned, &qb, n)); LB(tmp_alloc(owned, &counters, 2));
@@ -382,7 +386,7 @@ cudaError_t build_lbvh_device(const B200rtSphere *d_sph, uint32_t n_sph, const B
         LB(cudaMemsetAsync(counters, 0, sizeof(uint32_t), 0));
         LB(cudaStreamSynchronize(0));
         std::swap(qa, qb);
-        if (depth > 512) { cudaFreeAsync(nodes4, 0); return fail(cudaErrorUnknown); }
+        if (depth > 512) return fail(cudaErrorUnknown);
     }
     uint32_t n_nodes = 0;
     LB(cudaMemcpyAsync(&n_nodes, counters + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, 0));

@@ -41,16 +41,22 @@ __device__ __forceinline__ void sample_unit_sphere(float u1, float u2, double &x
     z = (double)cz;
 }
 
+// Uniform point in the unit disk from two uniforms (what random_vector_in_unit_disk() produces, vec3d.h:79-85).
+__device__ __forceinline__ void sample_unit_disk(float u1, float u2, double &x, double &y) {
+    const float rad = sqrtf(u1);
+    float s, c;
+    sincospif(2.0f * u2, &s, &c);
+    x = (double)(rad * c);
+    y = (double)(rad * s);
+}
+
 // camera.h:184-200 (+ :160-168 for the defocus disk)
 __device__ __forceinline__ void camera_ray(const CameraParams &C, uint32_t px, uint32_t py, const Philox4 &rnd,
                                            Ray &r, PathState &p) {
     double ox = C.center[0], oy = C.center[1], oz = C.center[2];
     if (C.defocus) {
-        // uniform point in the unit disk (random_vector_in_unit_disk, vec3d.h:79-85)
-        const float rad = sqrtf(u01(rnd.z));
-        float s, c;
-        sincospif(2.0f * u01(rnd.w), &s, &c);
-        const double ax = (double)(rad * c), ay = (double)(rad * s);
+        double ax, ay;
+        sample_unit_disk(u01(rnd.z), u01(rnd.w), ax, ay);
         ox = (C.center[0] + ax * C.disk_x[0]) + ay * C.disk_y[0];
         oy = (C.center[1] + ax * C.disk_x[1]) + ay * C.disk_y[1];
         oz = (C.center[2] + ax * C.disk_x[2]) + ay * C.disk_y[2];
@@ -89,6 +95,9 @@ __device__ __forceinline__ bool shade_hit(const DeviceScene &S, const Hit &h, co
     const bool inside = (r.dx * nx + r.dy * ny + r.dz * nz) > 0;
     if (inside) { nx = -nx; ny = -ny; nz = -nz; }
 
+#ifdef B200RT_DEBUG_BOUNDS
+    if (!B200RT_CHECK(S, mat_id < S.dbg.n_materials, 2)) return false;
+#endif
     const float4 m0 = __ldg((const float4 *)(S.materials + mat_id));
     const uint32_t kind = __float_as_uint(m0.w);
     if (kind == 3u) {   // DiffuseLight: emits on both faces, never scatters (material.h:248-263)

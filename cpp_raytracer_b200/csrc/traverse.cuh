@@ -26,6 +26,20 @@ struct DeviceMaterial {   // 32 B, two 16-byte loads
     double pad;
 };
 
+// -DB200RT_DEBUG_BOUNDS: the bounds-checked build the GPU test-suite runs in place of compute-sanitizer (which the
+// GPU pool does not allow).  Every traversal-stack push, node / primitive / material index and frame store is
+// range-checked; a violation is COUNTED (b200rt_debug_bounds) and the access skipped, so a broken tree shows up as
+// a failed test instead of silent corruption.  Slots: 0 stack, 1 node index, 2 primitive / material index, 3 pixel.
+#ifdef B200RT_DEBUG_BOUNDS
+struct DebugBounds {
+    unsigned long long *viol;   // [4]
+    uint32_t n_nodes, n_spheres, n_quads, n_materials, stack_cap;
+};
+#define B200RT_CHECK(S, cond, slot) ((cond) ? true : (atomicAdd((S).dbg.viol + (slot), 1ull), false))
+#else
+#define B200RT_CHECK(S, cond, slot) true
+#endif
+
 struct DeviceScene {
     const float4 *nodes;        // 8 x float4 per 4-wide node (bvh_builder.h Node4)
     const double2 *spheres;     // 2 x double2 per sphere, leaf order: {cx, cy}, {cz, r}
@@ -33,6 +47,9 @@ struct DeviceScene {
     const double2 *quads;       // 8 x double2 per quad, leaf order: n^[3] V[3] w[3] s1[3] s2[3] pad
     const uint2 *quad_meta;
     const DeviceMaterial *materials;
+#ifdef B200RT_DEBUG_BOUNDS
+    DebugBounds dbg;
+#endif
 };
 
 constexpr uint32_t kLeafFlagD = 0x80000000u;
@@ -50,6 +67,9 @@ struct TraversalCounters {
 };
 
 __device__ __forceinline__ uint32_t canonical_prim(const DeviceScene &S, uint32_t ref) {
+#ifdef B200RT_DEBUG_BOUNDS
+    if (!B200RT_CHECK(S, (ref & kQuadFlagD) ? (ref & ~kQuadFlagD) < S.dbg.n_quads : ref < S.dbg.n_spheres, 2)) return 0xFFFFFFFFu;
+#endif
     return (ref & kQuadFlagD) ? __ldg(&S.quad_meta[ref & ~kQuadFlagD]).x : __ldg(&S.sphere_meta[ref]).x;
 }
 
@@ -221,6 +241,9 @@ __device__ __forceinline__ void trav_pop(Trav &T, const uint2 *stack) {
 __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, uint2 *stack) {
     // Nodes are 128-byte aligned (checked at scene creation), so the six plane addresses are formed without
     // carries: near = base | (0/16, 32/48, 64/80), far = near ^ 16 -- one logic op each on the low word.
+#ifdef B200RT_DEBUG_BOUNDS
+    if (!B200RT_CHECK(S, T.cur < S.dbg.n_nodes, 1)) { trav_pop(T, stack); return; }
+#endif
     const uintptr_t base = reinterpret_cast<uintptr_t>(S.nodes) + ((uintptr_t)T.cur << 7);
     const uintptr_t pnx = base | T.near_off[0], pny = base | T.near_off[1], pnz = base | T.near_off[2];
 #define B200RT_NODE_F4(a) __ldg(reinterpret_cast<const float4 *>(a))
@@ -250,14 +273,14 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, ui
     // lanes of a warp serialise), and the node step is bound by the ALU pipe (88 of its ~150 instructions;
     // the pipe issues one warp instruction every 2 cycles), not by the load/store unit.
 #define B200RT_CHILD(key) __ldg(reinterpret_cast<const uint32_t *>((base | (uint32_t)(((key) << 2) & 0xCu)) + 96))
+#define B200RT_PUSH(key) if (key != 0xFFFFFFFFu && B200RT_CHECK(S, (uint32_t)T.sp < S.dbg.stack_cap, 0)) stack[T.sp++] = make_uint2(B200RT_CHILD(key), key);
     if (key0 != 0xFFFFFFFFu) {
-        if (key3 != 0xFFFFFFFFu) stack[T.sp++] = make_uint2(B200RT_CHILD(key3), key3);
-        if (key2 != 0xFFFFFFFFu) stack[T.sp++] = make_uint2(B200RT_CHILD(key2), key2);
-        if (key1 != 0xFFFFFFFFu) stack[T.sp++] = make_uint2(B200RT_CHILD(key1), key1);
+        B200RT_PUSH(key3) B200RT_PUSH(key2) B200RT_PUSH(key1)
         T.cur = B200RT_CHILD(key0);
     } else {
         trav_pop(T, stack);
     }
+#undef B200RT_PUSH
 #undef B200RT_CHILD
 }
 
@@ -265,6 +288,9 @@ __device__ __forceinline__ void trav_node_step(const DeviceScene &S, Trav &T, ui
 __device__ __forceinline__ uint32_t trav_leaf_step(const DeviceScene &S, Trav &T, const uint2 *stack) {
     const uint32_t cnt = (T.cur >> 26) & 0xFu, first = T.cur & 0x03FFFFFFu;
     const bool is_quad = T.cur & kQuadFlagD;
+#ifdef B200RT_DEBUG_BOUNDS
+    if (!B200RT_CHECK(S, first + cnt <= (is_quad ? S.dbg.n_quads : S.dbg.n_spheres), 2)) { trav_pop(T, stack); return 0; }
+#endif
     for (uint32_t i = 0; i < cnt; ++i) {
         double t;
         bool hit;

@@ -91,11 +91,13 @@ class FrameRenderer:
         self.ldr = ldr if ldr is not None else torch.empty((self.h, self.w, 3), dtype=torch.int32, device=self.device)
 
     def render_sum(self, want_stats: bool = False):
+        """This rank's samples as a SUM frame.  FLAG_EXACT_COUNT: a rank whose share is empty (spp < world) renders
+        nothing and gets a zero frame -- without it sample_count = 0 would mean "all of camera.spp"."""
         from . import capi
         stream = self.torch.cuda.current_stream(self.device).cuda_stream
         return self.scene.render_device(self.cam, self.frame.data_ptr(), stream=stream, seed=self.seed,
                                         sample_offset=self.first, sample_count=self.count, variant=self.variant,
-                                        flags=capi.FLAG_SUM, want_stats=want_stats)
+                                        flags=capi.FLAG_SUM | capi.FLAG_EXACT_COUNT, want_stats=want_stats)
 
     def finish(self, tonemap: bool = True):
         from . import capi

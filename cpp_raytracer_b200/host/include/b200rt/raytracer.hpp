@@ -537,6 +537,36 @@ inline bool flatten(const Scene &world, FlatScene &out, std::string &err) {
 
 }  // namespace b200rt_host
 
+namespace b200rt_host {
+// The GPUs a render uses when the program does not say (Camera::set_devices / the BVH constructor): the environment
+// variable B200RT_DEVICES -- "all", a count ("8" = devices 0..7) or a comma-separated list of CUDA ordinals ("0,2,3");
+// unset or unparsable = device 0.  This is how an UNMODIFIED reference program reaches config 5's sample split across
+// 8 x B200: B200RT_DEVICES=all ./raytracer.
+inline std::vector<int32_t> default_devices() {
+    std::vector<int32_t> out;
+    const char *env = std::getenv("B200RT_DEVICES");
+    if (env && *env) {
+        const std::string v = env;
+        const int have = b200rt_device_count();
+        if (v == "all") {
+            for (int d = 0; d < have; ++d) out.push_back(d);
+        } else if (v.find(',') == std::string::npos) {
+            const int n = std::atoi(v.c_str());
+            for (int d = 0; d < n; ++d) out.push_back(d);
+        } else {
+            size_t pos = 0;
+            while (pos <= v.size()) {
+                const size_t comma = std::min(v.find(',', pos), v.size());
+                if (comma > pos) out.push_back(std::atoi(v.substr(pos, comma - pos).c_str()));
+                pos = comma + 1;
+            }
+        }
+    }
+    if (out.empty()) out.push_back(0);
+    return out;
+}
+}  // namespace b200rt_host
+
 // ===== acceleration/bvh.h =====================================================================
 // BVH(world) (bvh.h:754-776) = the scene made resident on the GPU: primitives flattened, the wide BVH built
 // (host SAH or device LBVH by size) and uploaded, ONCE; every Camera::render(bvh) / hit_by afterwards reuses
@@ -555,8 +585,9 @@ public:
     // the device leaf format holds at most 8) and their reference defaults select the library's own.
     template <typename T>
         requires std::is_base_of_v<Hittable, T>
-    BVH(const T &world, size_t num_buckets = 32, size_t max_primitives_in_node = 12, int device = 0)
+    BVH(const T &world, size_t num_buckets = 32, size_t max_primitives_in_node = 12, std::vector<int32_t> devices = {})
         : primitives{world.get_primitive_components()} {
+        if (devices.empty()) devices = b200rt_host::default_devices();
         Scene flat_world;
         if (primitives.empty()) primitives.push_back(std::shared_ptr<Hittable>(std::shared_ptr<Hittable>{}, const_cast<T *>(&world)));
         for (const auto &p : primitives) flat_world.add(p);
@@ -568,12 +599,15 @@ public:
         }
         std::cout << "Building BVH over " << primitives.size() << " primitives..." << std::endl;
         B200rtBuildOpts opts{};
-        opts.device = device;
+        opts.device = devices[0];
         if (num_buckets != 32) opts.sah_bins = (int32_t)num_buckets;
         if (max_primitives_in_node != 12) opts.max_leaf_prims = (int32_t)max_primitives_in_node;
         const B200rtSceneDesc desc = flat.desc();
         dev = std::make_shared<Resident>();
-        if (b200rt_scene_create(&desc, &opts, &dev->handle) != B200RT_OK || b200rt_scene_info(dev->handle, &dev->info) != B200RT_OK) {
+        // one device: a plain resident scene; several: built once on devices[0] and copied to the others, and every
+        // Camera::render(bvh) splits the samples of each pixel across them inside the library
+        if (b200rt_scene_create_multi(&desc, &opts, devices.data(), (int32_t)devices.size(), &dev->handle) != B200RT_OK ||
+            b200rt_scene_info(dev->handle, &dev->info) != B200RT_OK) {
             std::cout << "Error: In BVH::BVH(), " << b200rt_last_error() << std::endl;
             std::exit(-1);
         }
@@ -633,6 +667,7 @@ class Camera {
     std::optional<double> vertical_fov{90}, horizontal_fov;                                     // camera.h:78 (sic: 90 radians)
     RGB background{RGB::from_mag(0.5)};
     uint64_t rng_seed = 0xB200;
+    std::vector<int32_t> devices;                                                               // empty: B200RT_DEVICES, else device 0
     B200rtStats last_stats{};
     B200rtSceneInfo last_info{};
 
@@ -738,7 +773,8 @@ public:
         std::vector<float> hdr(image_w * image_h * 3);
         std::cout << "Rendering " << image_w << " x " << image_h << " image (" << flat.spheres.size() + flat.quads.size()
                   << " primitives, " << samples_per_pixel << " spp) on the GPU..." << std::endl;
-        if (b200rt_render_scene(&desc, &cam, &opts, nullptr, hdr.data(), &last_stats, &last_info) != B200RT_OK) {
+        const std::vector<int32_t> devs = devices.empty() ? b200rt_host::default_devices() : devices;
+        if (b200rt_render_scene_multi(&desc, &cam, &opts, nullptr, devs.data(), (int32_t)devs.size(), hdr.data(), &last_stats, &last_info) != B200RT_OK) {
             std::cout << "Error: In Camera::render(), " << b200rt_last_error() << std::endl;
             std::exit(-1);
         }
@@ -749,6 +785,10 @@ public:
     const B200rtStats &stats() const { return last_stats; }
     const B200rtSceneInfo &scene_info() const { return last_info; }
     Camera &set_rng_seed(uint64_t s) { rng_seed = s; return *this; }   // extension: the GPU RNG key
+    // extension: the GPUs render(const Scene&) splits the samples of every pixel across (CUDA ordinals; the
+    // acceleration structure is built once on the first and copied to the others).  Not called: B200RT_DEVICES.
+    Camera &set_devices(std::vector<int32_t> d) { devices = std::move(d); return *this; }
+    Camera &set_device_count(int n) { devices.clear(); for (int d = 0; d < n; ++d) devices.push_back(d); return *this; }
 
     // camera.h:308-406
     Camera &set_camera_center(const Point3D &p) { camera.origin = p; return *this; }

@@ -4,7 +4,7 @@
 // through Camera::render -> libb200rt.so and writes a P3 PPM like the reference's main().
 //
 //   b200rt_scenes <scene> [--w W] [--h H] [--spp S] [--depth D] dump <out.scene>
-//   b200rt_scenes <scene> [...] render <out.ppm>
+//   b200rt_scenes <scene> [...] [--gpus N] render <out.ppm>      (N GPUs: samples split inside libb200rt.so)
 #include <cstdio>
 #include <cstring>
 #include <fstream>
@@ -13,7 +13,7 @@
 
 int main(int argc, char **argv) {
     if (argc < 3) {
-        std::fprintf(stderr, "usage: b200rt_scenes <scene> [--w W --h H --spp S --depth D] (dump <file> | render <file.ppm>)\n");
+        std::fprintf(stderr, "usage: b200rt_scenes <scene> [--w W --h H --spp S --depth D --gpus N] (dump <file> | render <file.ppm>)\n");
         return 1;
     }
     std::streambuf *cout_buf = std::cout.rdbuf();
@@ -30,6 +30,7 @@ int main(int argc, char **argv) {
         else if (o == "--h") h = v;
         else if (o == "--spp") s.camera.set_samples_per_pixel(v);
         else if (o == "--depth") s.camera.set_max_depth(v);
+        else if (o == "--gpus") s.camera.set_device_count((int)v);
         else { std::fprintf(stderr, "unknown option %s\n", o.c_str()); return 1; }
         i += 2;
     }
@@ -55,8 +56,10 @@ int main(int argc, char **argv) {
     } else if (cmd == "render") {
         s.camera.render(s.world).send_as_ppm(path);
         const B200rtStats &st = s.camera.stats();
-        std::printf("{\"cmd\":\"render\",\"paths\":%llu,\"rays\":%llu,\"kernel_ms\":%.3f,\"total_ms\":%.3f,\"build_ms\":%.3f}\n",
-                    (unsigned long long)st.paths, (unsigned long long)st.rays, st.kernel_ms, st.total_ms, s.camera.scene_info().build_ms);
+        std::printf("{\"cmd\":\"render\",\"paths\":%llu,\"rays\":%llu,\"kernel_ms\":%.3f,\"total_ms\":%.3f,\"build_ms\":%.3f,"
+                    "\"devices\":%u,\"replicate_ms\":%.3f,\"exchange_ms\":%.3f,\"peer_exchange\":%u}\n",
+                    (unsigned long long)st.paths, (unsigned long long)st.rays, st.kernel_ms, st.total_ms, s.camera.scene_info().build_ms,
+                    st.n_devices, st.replicate_ms, st.exchange_ms, st.peer_exchange);
     } else {
         std::fprintf(stderr, "unknown command %s\n", cmd.c_str());
         return 1;

@@ -13,9 +13,13 @@
  * (never exit()s, unlike the reference's std::exit(-1) in image.h:39-42); the message is
  * available from b200rt_last_error() on the calling thread.  The caller owns every host
  * buffer; the library owns device memory behind the opaque scene handle.  Calls block until
- * their result is in the caller's buffer unless stated otherwise.  One handle may be used
- * from one host thread at a time.  There is NO CPU fallback: without a CUDA device every
- * compute entry point fails with B200RT_ENODEVICE.
+ * their result is in the caller's buffer unless stated otherwise.  A scene handle is NOT re-entrant:
+ * calls on one handle are serialised inside the library (a mutex per handle); different handles
+ * may be used from different host threads concurrently.  Device memory comes from a private
+ * stream-ordered pool per device (the process-wide default pool is never touched); it keeps up to
+ * B200RT_POOL_KEEP_MB (environment, default 4096) MiB of freed memory for the next frame and
+ * b200rt_trim() returns it.  There is NO CPU fallback: without a CUDA device every compute entry
+ * point fails with B200RT_ENODEVICE.
  */
 #ifndef B200RT_H
 #define B200RT_H
@@ -26,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B200RT_VERSION 1
+#define B200RT_VERSION 2
 
 enum {
     B200RT_OK = 0,
@@ -106,14 +110,18 @@ typedef struct B200rtSceneInfo {
 } B200rtSceneInfo;
 
 enum {
-    B200RT_VARIANT_MEGAKERNEL = 0,          /* one thread per pixel, path regeneration (default) */
-    B200RT_VARIANT_WAVEFRONT = 1,           /* per-material ray queues */
-    B200RT_VARIANT_MEGAKERNEL_VOTED = 2     /* experiment: warp-voted node/leaf/shade step scheduling */
+    B200RT_VARIANT_MEGAKERNEL = 0,          /* one launch for the whole frame, path regeneration (default) */
+    B200RT_VARIANT_WAVEFRONT = 1            /* per-material ray queues */
+    /* 2 was an experiment (warp-voted step scheduling, measured slower: DESIGN.md section 7); it is no longer
+     * part of the library and is rejected with B200RT_EINVAL */
 };
 enum {
     B200RT_FLAG_SUM = 1,          /* write the per-pixel SUM over the samples of this call instead of the mean */
     B200RT_FLAG_ACCUMULATE = 2,   /* device entry only: add into the output buffer instead of overwriting */
-    B200RT_FLAG_COUNTERS = 4      /* also count node visits and primitive tests (slower; for roofline accounting) */
+    B200RT_FLAG_COUNTERS = 4,     /* also count node visits and primitive tests (slower; for roofline accounting) */
+    B200RT_FLAG_EXACT_COUNT = 8   /* sample_count is taken literally: 0 renders NO samples (the output is zeroed /
+                                     left alone under ACCUMULATE) instead of meaning "camera.spp" -- what a rank of a
+                                     sample split whose share is empty (spp < ranks) must pass */
 };
 
 typedef struct B200rtRenderOpts {
@@ -131,18 +139,41 @@ typedef struct B200rtStats {
     uint64_t node_visits, prim_tests;   /* only with B200RT_FLAG_COUNTERS */
     uint64_t kernel_launches;
     uint64_t h2d_bytes, d2h_bytes;
+    /* v2 */
+    double build_ms;           /* acceleration-structure build incl. the upload of the caller's arrays (one-call entries) */
+    double replicate_ms;       /* multi-GPU: copying the built scene to the other devices (peer copies, NVLink) */
+    double exchange_ms;        /* multi-GPU: summing the per-device frames onto the first device + scaling */
+    uint32_t n_devices;        /* devices that rendered */
+    uint32_t peer_exchange;    /* 1: fused peer-memory kernel (one launch per device); 0: copies + accumulate on the root */
 } B200rtStats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */
 int b200rt_device_count(void);
 const char *b200rt_last_error(void);
 int b200rt_version(void);
+/* Returns the freed device memory the library's private pools are holding to the driver (all devices). */
+int b200rt_trim(void);
 
 /* Replaces: BVH::BVH(world) + the pointer graph it keeps (bvh.h:754-776).  Flattens the
  * primitives into SoA device arrays, builds the wide BVH and uploads everything. */
 int b200rt_scene_create(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, void **scene_out);
 int b200rt_scene_info(void *scene, B200rtSceneInfo *info);
 void b200rt_scene_destroy(void *scene);
+
+/* The same scene made resident on SEVERAL GPUs of this process (SURVEY 8(b) "device list / nGPU", 8(e)): the
+ * acceleration structure is built ONCE on devices[0] and copied to the others device-to-device
+ * (cudaMemcpyPeerAsync: NVLink where the GPUs are peers).  The handle is accepted by b200rt_render
+ * (every device renders its share of the samples of every pixel, rank k of n takes samples
+ * [k*spp/n, (k+1)*spp/n) of the requested range; the per-device FP32 sum frames are added in device-list order
+ * onto devices[0] -- one fused kernel per device over peer-mapped memory when all pairs are peers, else
+ * copies + accumulate on devices[0] -- and scaled there; the image equals the single-GPU image up to FP32
+ * summation order), b200rt_scene_info, b200rt_raycast / b200rt_debug_shade (answered by devices[0]) and
+ * b200rt_scene_destroy.  n_devices == 1 is the same as b200rt_scene_create on that device;
+ * devices == NULL means devices 0 .. n_devices-1.  No torch, no NCCL, one host thread.
+ * Replaces: nothing in the reference (it has one CPU); this is how `Camera::render` reaches config 5,
+ * "sample-split across 8 x B200". */
+int b200rt_scene_create_multi(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, const int32_t *devices,
+                              int32_t n_devices, void **scene_out);
 
 /* Replaces: Camera::init() (camera.h:87-157).  Host, double precision. */
 int b200rt_camera_init(B200rtCamera *cam);
@@ -181,6 +212,33 @@ int b200rt_debug_shade(void *scene, const double *rays, const uint32_t *rnd, int
 int b200rt_debug_camera_rays(const B200rtCamera *cam, const uint32_t *pixels_xy, const uint32_t *rnd, int64_t n,
                              double *rays_out, int device);
 
+/* Test hooks for the two pieces no oracle can pin through images.  b200rt_debug_philox: the kernels' generator
+ * (Philox4x32-10, csrc/rng.cuh) evaluated ON THE DEVICE for n (counter[4], key[2]) inputs -> out = n x 4 words;
+ * checked against the Random123 known-answer vectors.  b200rt_debug_samplers: the kernels' direction samplers for n
+ * pairs of random words (u = (w >> 8) / 2^24): sphere_out = n x 3 doubles, the unit vector Lambertian / Metal add
+ * (stands in for random_unit_vector(), vec3d.h:64-75); disk_out = n x 2 doubles, the defocus-disk point (stands in
+ * for random_vector_in_unit_disk(), vec3d.h:79-85). */
+int b200rt_debug_philox(const uint32_t *counters_keys, int64_t n, uint32_t *out, int device);
+int b200rt_debug_samplers(const uint32_t *rnd_pairs, int64_t n, double *sphere_out, double *disk_out, int device);
+
+/* Bounds-checked build (-DB200RT_DEBUG_BOUNDS; the stand-in for compute-sanitizer, which the GPU pool does not
+ * allow): every traversal-stack push, node / primitive / material index and frame store is range-checked on the
+ * device; a violation is counted and the access skipped.  out[4] = {stack pushes beyond capacity, node index,
+ * primitive or material index, pixel index} violations since the scene was created.  Returns B200RT_EINVAL in a
+ * library built without the flag.  B200RT_DEBUG_STACK_CAP (environment, debug build only) lowers the stack
+ * capacity the check enforces, to prove the check is live. */
+int b200rt_debug_bounds(void *scene, uint64_t *out);
+
+/* Measurement hook: renders `cam` like b200rt_render's default kernel (same schedule: every round each lane of a warp
+ * shades / regenerates, then the warp runs one traversal step per lane per iteration until its slowest lane is done)
+ * with per-warp accounting of where the 32 lanes are at every executed step.  counters_out[16]:
+ *   [0] shade executions, [1] lanes taking part;
+ *   [2] node-step executions, [3] lanes at a node, idle lanes: [4] at a leaf, [5] traversal done (waiting for the
+ *       slowest lane of the round), [6] pixel out of samples;
+ *   [7] leaf-step executions, [8] lanes at a leaf, idle lanes: [9] at a node, [10] done, [11] out of samples;
+ *   [12] primitive-test executions, [13] lanes taking part; [14] warps; [15] rays.  No image is returned. */
+int b200rt_debug_lane_accounting(void *scene, const B200rtCamera *cam, const B200rtRenderOpts *opts, uint64_t *counters_out);
+
 /* ---- render ---------------------------------------------------------------------------- */
 /* Replaces: Camera::render<BVH>(bvh) (camera.h:264-297): for every pixel, the mean (or sum)
  * over the requested samples of ray_color (camera.h:205-258).  out_rgb = image_h x image_w x 3
@@ -200,6 +258,12 @@ int b200rt_render_device(void *scene, const B200rtCamera *cam, const B200rtRende
 int b200rt_render_scene(const B200rtSceneDesc *desc, const B200rtCamera *cam,
                         const B200rtRenderOpts *opts, const B200rtBuildOpts *bopts,
                         float *out_rgb, B200rtStats *stats, B200rtSceneInfo *info);
+
+/* Camera::render(const Scene &) end to end on several GPUs: b200rt_scene_create_multi + b200rt_render +
+ * destroy in one call on host buffers. */
+int b200rt_render_scene_multi(const B200rtSceneDesc *desc, const B200rtCamera *cam, const B200rtRenderOpts *opts,
+                              const B200rtBuildOpts *bopts, const int32_t *devices, int32_t n_devices,
+                              float *out_rgb, B200rtStats *stats, B200rtSceneInfo *info);
 
 /* ---- tone map --------------------------------------------------------------------------- */
 /* Replaces: RGB::as_string() defaults (rgb.h:90-113): Reinhard by luminance, gamma 2,

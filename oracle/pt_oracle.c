@@ -203,6 +203,29 @@ static V3 random_unit_vector(uint32_t *rng) {                                   
     return vunit(r);
 }
 
+static V3 random_vector_in_unit_disk(uint32_t *rng) {                            /* vec3d.h:79-85 */
+    V3 v;
+    do {
+        v.x = oracle_rand_double(rng, -1, 1);
+        v.y = oracle_rand_double(rng, -1, 1);
+        v.z = 0;
+    } while (!(vmag2(v) < 1));
+    return v;
+}
+
+/* n draws of the two rejection samplers from one LCG stream (test hooks for the distribution tests of the
+ * device's direct samplers; the same two functions feed oracle_render, whose bit-exact match with the reference
+ * pins them). */
+void oracle_random_unit_vectors(uint32_t *lcg_state, int64_t n, double *out) {
+    for (int64_t i = 0; i < n; ++i) to(out + 3 * i, random_unit_vector(lcg_state));
+}
+void oracle_random_vectors_in_unit_disk(uint32_t *lcg_state, int64_t n, double *out) {
+    for (int64_t i = 0; i < n; ++i) {
+        V3 v = random_vector_in_unit_disk(lcg_state);
+        out[2 * i] = v.x; out[2 * i + 1] = v.y;
+    }
+}
+
 typedef struct { double r, g, b; } RGBd;
 static RGBd rgb(double r, double g, double b) { RGBd c = {r, g, b}; return c; }
 
@@ -280,13 +303,7 @@ uint64_t oracle_render(const OScene *scene, const OCamera *c, uint32_t *lcg_stat
             RGBd px = rgb(0, 0, 0);
             for (uint64_t s = 0; s < c->spp; ++s) {
                 V3 v = {0, 0, 0};                                                /* camera.h:184-200 */
-                if (!(c->defocus_angle <= 0)) {
-                    do {                                                         /* vec3d.h:79-85 */
-                        v.x = oracle_rand_double(cx.rng, -1, 1);
-                        v.y = oracle_rand_double(cx.rng, -1, 1);
-                        v.z = 0;
-                    } while (!(vmag2(v) < 1));
-                }
+                if (!(c->defocus_angle <= 0)) v = random_vector_in_unit_disk(cx.rng);
                 /* camera.h:197-198: `pc + rand*dx + rand*dy` -- the two draws are unsequenced in C++;
                  * g++ 13 (the compiler the reference is built with here) evaluates the right-hand
                  * operand first, i.e. the delta_y factor is drawn BEFORE the delta_x factor.  Pinned by

@@ -46,6 +46,10 @@ double oracle_reflectance(double cos_theta, double ratio);
 void oracle_camera_ray(const OCamera *cam, uint64_t row, uint64_t col, double vx, double vy, double r1, double r2, double out[6]);
 uint64_t oracle_render(const OScene *scene, const OCamera *cam, uint32_t *lcg_state, double *out_rgb);
 
+/* vec3d.h:64-85: n draws of random_unit_vector() (n x 3) / random_vector_in_unit_disk() (n x 2) */
+void oracle_random_unit_vectors(uint32_t *lcg_state, int64_t n, double *out);
+void oracle_random_vectors_in_unit_disk(uint32_t *lcg_state, int64_t n, double *out);
+
 /* rgb.h:90-113 */
 void oracle_tonemap(const double *rgb, int64_t n_pixels, int32_t *out);
 

@@ -46,6 +46,8 @@ def lib():
         l.oracle_camera_ray.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
         l.oracle_camera_ray.restype = None
         l.oracle_tonemap.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
+        l.oracle_random_unit_vectors.argtypes = [C.POINTER(C.c_uint32), C.c_int64, C.c_void_p]
+        l.oracle_random_vectors_in_unit_disk.argtypes = [C.POINTER(C.c_uint32), C.c_int64, C.c_void_p]
         _lib = l
     return _lib
 
@@ -122,6 +124,22 @@ def render(scene, cam, lcg_state: int):
     osc = _oscene(scene)
     rays = lib().oracle_render(C.byref(osc), cam.ctypes.data, C.byref(st), out.ctypes.data)
     return out, int(rays), st.value
+
+
+def random_unit_vectors(n: int, lcg_state: int = 12345) -> np.ndarray:
+    """n draws of Vec3D::random_unit_vector() (vec3d.h:64-75, rejection + normalise) from the reference's LCG."""
+    out = np.empty((n, 3), np.float64)
+    st = C.c_uint32(lcg_state)
+    lib().oracle_random_unit_vectors(C.byref(st), n, out.ctypes.data)
+    return out
+
+
+def random_vectors_in_unit_disk(n: int, lcg_state: int = 12345) -> np.ndarray:
+    """n draws of Vec3D::random_vector_in_unit_disk() (vec3d.h:79-85)."""
+    out = np.empty((n, 2), np.float64)
+    st = C.c_uint32(lcg_state)
+    lib().oracle_random_vectors_in_unit_disk(C.byref(st), n, out.ctypes.data)
+    return out
 
 
 def tonemap(rgb):

@@ -49,3 +49,22 @@ def test_sample_split_reduce_world2_gloo(tmp_path):
     got = np.load(out)
     want = _frame_sum(h, w, 0, spp) / spp
     assert np.allclose(got, want, rtol=1e-5, atol=1e-6)
+
+
+def test_sample_split_with_fewer_samples_than_ranks():
+    """spp < world gives some ranks an EMPTY share; the shares must still tile [0, spp) exactly
+    (FrameRenderer passes B200RT_FLAG_EXACT_COUNT so that count == 0 renders nothing instead of meaning "camera.spp";
+    the device side of that is tests/test_gpu_multi.py::test_exact_count_zero_renders_nothing)."""
+    from cpp_raytracer_b200 import capi
+    from cpp_raytracer_b200.dist import sample_range
+    for spp, world in [(4, 8), (1, 8), (0, 2), (3, 2), (7, 4), (1024, 8), (37, 2)]:
+        covered = []
+        for r in range(world):
+            lo, n = sample_range(spp, r, world)
+            assert n >= 0
+            covered += list(range(lo, lo + n))
+        assert covered == list(range(spp)), (spp, world)
+    assert capi.FLAG_EXACT_COUNT == 8
+    import inspect
+    from cpp_raytracer_b200 import dist as rtdist
+    assert "FLAG_EXACT_COUNT" in inspect.getsource(rtdist.FrameRenderer.render_sum)

@@ -1,0 +1,124 @@
+"""Single-process multi-GPU render behind the C ABI (b200rt_scene_create_multi / b200rt_render_scene_multi,
+VERDICT r1 task 2): the scene is built once on devices[0] and copied to the others, every device renders its share
+of the samples of every pixel, the frames are summed in device order onto devices[0].  No torch, no NCCL.
+Reference: the one call all of this stands behind is Camera::render(const Scene&), include/base/camera.h:301-303.
+
+Tests that need two GPUs skip on a one-GPU box; the handle plumbing (a one-device "list", argument checking, the
+EXACT_COUNT flag a sample split needs) runs on one."""
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def n_gpus():
+    from cpp_raytracer_b200 import capi
+    return capi.device_count()
+
+
+def test_device_list_of_one_is_the_plain_scene(golden):
+    import cpp_raytracer_b200 as rt
+    scene = golden.scene("rtow_lights")
+    cam = rt.camera_with(scene.camera, image_w=80, image_h=45, spp=16)
+    with rt.DeviceSceneHandle(scene, device=0) as a, rt.DeviceSceneHandle(scene, devices=[0]) as b:
+        ia, sa = a.render(cam, seed=9)
+        ib, sb = b.render(cam, seed=9)
+        assert np.array_equal(ia, ib) and sa["rays"] == sb["rays"] and sb["n_devices"] == 1
+    ic, sc, info = rt.render_scene(scene, cam, seed=9, devices=[0])
+    assert np.array_equal(ia, ic) and info["n_prims"] == scene.n_prims
+
+
+def test_multi_argument_checking(golden):
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    scene = golden.scene("quads")
+    for bad in ([], [0, 0], [-1], [n_gpus()], list(range(17))):
+        with pytest.raises(capi.B200rtError) as e:
+            rt.DeviceSceneHandle(scene, devices=bad)
+        assert e.value.code == capi.EINVAL, bad
+
+
+def test_exact_count_zero_renders_nothing(golden):
+    """sample_count == 0 means "camera.spp" -- unless FLAG_EXACT_COUNT says it is literal, which is
+    what a rank with an empty share of a sample split (spp < ranks) passes: zero frame, no rays."""
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    scene = golden.scene("rtow_lights")
+    cam = rt.camera_with(scene.camera, image_w=40, image_h=30, spp=4)
+    with rt.DeviceSceneHandle(scene) as dev:
+        full, st = dev.render(cam, seed=1, sample_count=0, flags=capi.FLAG_SUM)
+        assert st["paths"] == 40 * 30 * 4 and full.max() > 0
+        none, st0 = dev.render(cam, seed=1, sample_count=0, flags=capi.FLAG_SUM | capi.FLAG_EXACT_COUNT)
+        assert st0["paths"] == 0 and st0["rays"] == 0 and not none.any()
+        # the shares of an 8-way split of 4 samples (four of them empty) add up to the whole
+        total = np.zeros_like(full)
+        for k in range(8):
+            lo, hi = 4 * k // 8, 4 * (k + 1) // 8
+            part, _ = dev.render(cam, seed=1, sample_offset=lo, sample_count=hi - lo, flags=capi.FLAG_SUM | capi.FLAG_EXACT_COUNT)
+            total += part
+        assert np.allclose(total, full, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["rtow_lights", "cornell"])
+def test_multi_gpu_frame_equals_single_gpu_frame(golden, name):
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import cpp_raytracer_b200 as rt
+    scene = golden.scene(name)
+    n = min(n_gpus(), 8)
+    cam = rt.camera_with(scene.camera, image_w=200, image_h=120, spp=37, max_depth=20)   # 37: ragged shares
+    with rt.DeviceSceneHandle(scene, device=0) as one:
+        want, s1 = one.render(cam, seed=21)
+    for devs in ([0, 1], list(range(n)), [1, 0]):
+        with rt.DeviceSceneHandle(scene, devices=devs) as multi:
+            got, sm = multi.render(cam, seed=21)
+            again, _ = multi.render(cam, seed=21)
+        assert sm["n_devices"] == len(devs) and sm["rays"] == s1["rays"] and sm["paths"] == s1["paths"]
+        assert np.array_equal(got, again)                                       # deterministic
+        # same paths, same per-sample radiance; only the FP32 order of the per-device partial sums differs
+        assert np.allclose(got, want, rtol=2e-5, atol=1e-6), (name, devs, float(np.abs(got - want).max()))
+    # spp smaller than the device count: some devices get an empty share
+    cam2 = rt.camera_with(scene.camera, image_w=64, image_h=40, spp=1)
+    with rt.DeviceSceneHandle(scene, device=0) as one:
+        want2, _ = one.render(cam2, seed=4)
+    got2, st2, _ = rt.render_scene(scene, cam2, seed=4, devices=list(range(n)))
+    assert np.allclose(got2, want2, rtol=2e-5, atol=1e-6) and st2["n_devices"] == n
+
+
+def test_multi_gpu_big_scene_is_built_once_and_copied(tmp_path):
+    """The 2.2 M-quad scene through the one-call entry on all GPUs: the GPU-built tree on devices[0] is copied to the
+    others (replicate_ms, not N builds) and the frame matches the one-GPU frame."""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import build, scene_io
+    p = str(tmp_path / "s.scene")
+    subprocess.run([build.build_host(), "raining", "dump", p], check=True, capture_output=True)
+    scene = scene_io.load_scene(p)
+    cam = rt.camera_with(scene.camera, image_w=320, image_h=180, spp=16)
+    want, s1, _ = rt.render_scene(scene, cam, seed=3, devices=[0])
+    got, sm, info = rt.render_scene(scene, cam, seed=3, devices=list(range(min(n_gpus(), 8))))
+    assert sm["rays"] == s1["rays"] and np.allclose(got, want, rtol=2e-5, atol=1e-6)
+    print(f"raining on {sm['n_devices']} GPUs: build {sm['build_ms']:.1f} ms, replicate {sm['replicate_ms']:.1f} ms, "
+          f"exchange {sm['exchange_ms']:.3f} ms (peer kernel: {sm['peer_exchange']}), total {sm['total_ms']:.1f} ms")
+
+
+def test_host_cpp_program_renders_on_all_gpus(tmp_path):
+    """`b200rt_scenes <scene> --gpus N render`: Camera::set_device_count -> b200rt_render_scene_multi from C++."""
+    if n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from cpp_raytracer_b200 import build
+    a, b = str(tmp_path / "a.ppm"), str(tmp_path / "b.ppm")
+    args = ["rtow_lights", "--w", "96", "--h", "54", "--spp", "32"]
+    r1 = subprocess.run([build.build_host(), *args, "--gpus", "1", "render", a], capture_output=True, text=True)
+    r2 = subprocess.run([build.build_host(), *args, "--gpus", "2", "render", b], capture_output=True, text=True)
+    assert r1.returncode == 0 and r2.returncode == 0, r1.stderr + r2.stderr
+    j2 = json.loads(r2.stdout.strip().splitlines()[-1])
+    assert j2["devices"] == 2
+    ia = np.array(open(a).read().split()[4:], dtype=np.int32)
+    ib = np.array(open(b).read().split()[4:], dtype=np.int32)
+    assert np.abs(ia - ib).max() <= 1                                           # tone-mapped integers: FP32 summation order only

@@ -127,6 +127,58 @@ def test_raycast_vs_c_oracle_on_seeded_random_scenes(seed, n_sph, n_quad, leaf):
     assert np.array_equal(p, want_p) and np.array_equal(t, want_t)
 
 
+@pytest.mark.parametrize("seed,scale,rmin,rmax,builder", [(11, 1e3, 1e-3, 5.0, 1), (12, 1e6, 1e-3, 50.0, 1), (13, 1e6, 1e-3, 1e4, 2),
+                                                          (14, 1e4, 1e-2, 1e6, 1), (15, 1e5, 1e-3, 1.0, 2)])
+def test_conservative_boxes_hold_at_large_coordinates_and_tiny_radii(seed, scale, rmin, rmax, builder):
+    """Fuzz of the conservative FP32 slab test (traverse.cuh: bounds rounded outward, o/d products formed in double and
+    padded, multiplicative slack): 1.05 M rays per case on random scenes whose coordinates reach +-`scale` (1e3 ... 1e6)
+    with radii down to 1e-3 and up to 1e6 (log-uniform), under both builders.  A box test that pruned a node it should
+    not have would show as a hit the brute-force oracle (oracle/pt_oracle.c, Scene::hit_by semantics,
+    reference scene.h:59-75) finds and the device misses.  Rays are aimed at primitives (so that tiny far spheres are
+    actually hit), through them from inside, along axes, and at random."""
+    import os, sys
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    from conftest import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pt_oracle
+    rng = np.random.default_rng(seed)
+    n_sph, n_quad = 96, 32
+    sph = np.zeros(n_sph, capi.SPHERE_DTYPE)
+    sph["c"] = rng.uniform(-scale, scale, (n_sph, 3))
+    sph["r"] = np.exp(rng.uniform(np.log(rmin), np.log(rmax), n_sph))
+    quads = np.zeros(n_quad, capi.QUAD_DTYPE)
+    quads["v"] = rng.uniform(-scale, scale, (n_quad, 3))
+    qs = np.exp(rng.uniform(np.log(max(rmin, 1e-2)), np.log(rmax), (n_quad, 1)))
+    quads["s1"] = rng.normal(size=(n_quad, 3)) * qs
+    quads["s2"] = rng.normal(size=(n_quad, 3)) * qs
+    order = rng.permutation(n_sph + n_quad)
+    sph["prim"], quads["prim"] = order[:n_sph], order[n_sph:]
+    scene = capi.HostScene(np.zeros(1, capi.MATERIAL_DTYPE), sph, quads, np.zeros(1, capi.CAMERA_DTYPE))
+    n = 1_050_000
+    o = rng.uniform(-scale, scale, (n, 3))
+    # targets: a point inside a random sphere (70 %), on a random quad (20 %), or anywhere (10 %)
+    k = rng.integers(0, n_sph, n)
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    tgt = sph["c"][k] + u * (sph["r"][k] * rng.uniform(0, 0.999, n))[:, None]
+    qk = rng.integers(0, n_quad, n)
+    on_quad = quads["v"][qk] + quads["s1"][qk] * rng.uniform(0, 1, (n, 1)) + quads["s2"][qk] * rng.uniform(0, 1, (n, 1))
+    kind = rng.uniform(size=n)
+    tgt = np.where((kind < 0.7)[:, None], tgt, np.where((kind < 0.9)[:, None], on_quad, rng.uniform(-scale, scale, (n, 3))))
+    inside = rng.uniform(size=n) < 0.1                      # 10 %: start inside the target sphere
+    o[inside] = (sph["c"][k] + u * (sph["r"][k] * 0.5)[:, None])[inside]
+    d = (tgt - o) * np.exp(rng.uniform(np.log(1e-3), np.log(1e3), (n, 1)))      # unnormalised, |d| over six decades
+    axis = rng.uniform(size=n) < 0.05                       # 5 %: axis-parallel (zero components)
+    d[axis] = np.eye(3)[rng.integers(0, 3, axis.sum())] * rng.choice([-1.0, 1.0], axis.sum())[:, None] * scale
+    rays = np.concatenate([o, d], axis=1)
+    want_p, want_t = pt_oracle.raycast_brute(scene, rays, 1e-5, np.inf)
+    with rt.DeviceSceneHandle(scene, builder=builder) as dev:
+        p, t = dev.raycast(rays, 1e-5, np.inf)
+    assert (want_p >= 0).mean() > 0.3, "the ray set must actually hit things"
+    bad = np.nonzero((p != want_p) | (t != want_t))[0]
+    assert len(bad) == 0, (len(bad), rays[bad[:3]], p[bad[:3]], want_p[bad[:3]], t[bad[:3]], want_t[bad[:3]])
+
+
 def test_raycast_exact_ties_resolve_to_lowest_canonical_index():
     """Coincident primitives: the lowest canonical index wins (Scene::hit_by, scene.h:59-75),
     whatever order the tree visits them in."""

@@ -25,7 +25,9 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libb200rt.so does not export {n}"
     assert sorted(capi.EXPORTS) == names, "capi.EXPORTS and include/b200rt.h disagree"
-    assert lib.b200rt_version() == 1
+    assert lib.b200rt_version() == 2      # B200RT_VERSION: v2 added the multi-device entries and the Stats tail
+    src = open(os.path.join(ROOT, "include", "b200rt.h")).read()
+    assert "#define B200RT_VERSION 2" in src
 
 
 def test_struct_layouts_match_header():
