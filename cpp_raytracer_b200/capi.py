@@ -67,7 +67,7 @@ class Stats(C.Structure):
                 ("paths", C.c_uint64), ("rays", C.c_uint64), ("node_visits", C.c_uint64), ("prim_tests", C.c_uint64),
                 ("kernel_launches", C.c_uint64), ("h2d_bytes", C.c_uint64), ("d2h_bytes", C.c_uint64),
                 ("build_ms", C.c_double), ("replicate_ms", C.c_double), ("exchange_ms", C.c_double),
-                ("n_devices", C.c_uint32), ("peer_exchange", C.c_uint32)]
+                ("n_devices", C.c_uint32), ("peer_exchange", C.c_uint32), ("quad_tests", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

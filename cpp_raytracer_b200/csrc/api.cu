@@ -26,8 +26,9 @@ using namespace b200rt;
 
 namespace b200rt {
 cudaError_t build_lbvh_device(const B200rtSphere *d_sph, uint32_t n_sph, const B200rtQuad *d_quads, uint32_t n_quad,
-                              double2 *out_sph, uint2 *out_sph_meta, double2 *out_quads, uint2 *out_quad_meta,
-                              float4 **nodes_out, uint32_t *n_nodes_out, uint32_t *depth_out);
+                              uint32_t n_materials, double2 *out_sph, uint2 *out_sph_meta, double2 *out_quads, uint2 *out_quad_meta,
+                              float4 **nodes_out, uint32_t *n_nodes_out, uint32_t *depth_out, int *bad_index_out);
+cudaError_t convert_materials_device(const B200rtMaterial *d_raw, uint32_t n, DeviceMaterial *d_out, int *bad_kind_out);
 }
 
 namespace {
@@ -73,9 +74,10 @@ struct SceneImpl {
     // [0] nodes, [1] spheres, [2] sphere_meta, [3] quads, [4] quad_meta, [5] materials
     void *allocs[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t alloc_bytes[6] = {0, 0, 0, 0, 0, 0};
+    bool peer_visible = false;       // the arrays are peer-visible buffers (devmem.h): a multi-device scene copies them device to device
     B200rtSceneInfo info{};
     int stack = 32;
-    unsigned long long *d_counters = nullptr;   // [0] rays, [1] node visits, [2] primitive tests
+    unsigned long long *d_counters = nullptr;   // [0] rays, [1] node visits, [2] primitive tests, [3] of which quad tests
     unsigned long long *d_viol = nullptr;       // bounds-checked build only: [4] violation counters
     float *d_frame = nullptr;        // scratch frame for the host-buffer render entry
     size_t frame_floats = 0;
@@ -101,6 +103,24 @@ struct MultiImpl {
     bool peers = false;                      // every device can dereference every other device's pool memory
     double replicate_ms = 0;
 };
+
+// Scene arrays: stream-ordered pool memory, or (multi-device scenes) peer-visible buffers.
+cudaError_t scene_alloc(SceneImpl *s, int slot, size_t bytes) {
+    void *p = nullptr;
+    const cudaError_t e = s->peer_visible ? peer_buffer_acquire(s->device, bytes, &p) : dev_alloc_async(&p, bytes, 0);
+    if (e != cudaSuccess) return e;
+    s->allocs[slot] = p;
+    s->alloc_bytes[slot] = bytes;
+    return cudaSuccess;
+}
+void scene_free_arrays(SceneImpl *s) {
+    for (int i = 0; i < 6; ++i) {
+        if (s->peer_visible) peer_buffer_release(s->device, s->allocs[i]);
+        else dev_free(s->allocs[i]);
+        s->allocs[i] = nullptr;
+        s->alloc_bytes[i] = 0;
+    }
+}
 
 SceneImpl *as_scene(void *h) {
     SceneImpl *s = static_cast<SceneImpl *>(h);
@@ -160,12 +180,13 @@ Box3 quad_box(const B200rtQuad &q) {       // parallelogram.h:281-295 + aabb.h e
     return b;
 }
 
-int validate_desc(const B200rtSceneDesc *d) {
+int validate_desc(const B200rtSceneDesc *d, bool check_prims = true) {
     if (!d) return fail(B200RT_EINVAL, "scene description is NULL");
     if ((d->n_materials && !d->materials) || (d->n_spheres && !d->spheres) || (d->n_quads && !d->quads))
         return fail(B200RT_EINVAL, "scene description has a count without an array");
     const uint64_t n_prims = d->n_spheres + d->n_quads;
     if (n_prims > 0x7FFFFFFFull) return fail(B200RT_EINVAL, "too many primitives");
+    if (!check_prims) return B200RT_OK;   // the GPU builder checks material kinds and per-primitive indices on the device
     for (uint64_t i = 0; i < d->n_materials; ++i)
         if (d->materials[i].kind > B200RT_MAT_LIGHT)
             return fail(B200RT_EINVAL, "unknown material kind " + std::to_string(d->materials[i].kind) +
@@ -212,15 +233,12 @@ BuildParams build_params(const B200rtBuildOpts *o) {
 }
 
 template <typename T>
-int upload(const std::vector<T> &host, const T **dev, void **slot, size_t *slot_bytes, uint64_t &bytes) {
+int upload(SceneImpl *s, int slot, const std::vector<T> &host, const T **dev, uint64_t &bytes) {
     *dev = nullptr;
     if (host.empty()) return B200RT_OK;
-    void *p = nullptr;
-    CUDA_TRY(dev_alloc(&p, host.size() * sizeof(T)));
-    *slot = p;                                     // owned by the scene from here on (freed by free_scene on any later failure)
-    *slot_bytes = host.size() * sizeof(T);
-    CUDA_TRY(staged_upload(p, host.data(), host.size() * sizeof(T), 0));
-    *dev = static_cast<const T *>(p);
+    CUDA_TRY(scene_alloc(s, slot, host.size() * sizeof(T)));   // owned by the scene from here on (free_scene releases it on any later failure)
+    CUDA_TRY(staged_upload(s->allocs[slot], host.data(), host.size() * sizeof(T), 0));
+    *dev = static_cast<const T *>(s->allocs[slot]);
     bytes += host.size() * sizeof(T);
     return B200RT_OK;
 }
@@ -229,7 +247,7 @@ void free_scene(SceneImpl *s) {
     if (!s) return;
     DeviceGuard g(s->device);
     cudaDeviceSynchronize();   // kernels of any stream may still read the scene
-    for (void *&p : s->allocs) { dev_free(p); p = nullptr; }
+    scene_free_arrays(s);
     dev_free(s->d_counters);
     dev_free(s->d_viol);
     dev_free(s->d_frame);
@@ -250,7 +268,7 @@ void free_multi(MultiImpl *m) {
         if (!m->dev[i]) continue;
         DeviceGuard g(m->dev[i]->device);
         if (i < m->stream.size() && m->stream[i]) cudaStreamSynchronize(m->stream[i]);
-        if (i < m->frame.size()) dev_free(m->frame[i]);
+        if (i < m->frame.size()) peer_buffer_release(m->dev[i]->device, m->frame[i]);
         if (i == 0) dev_free(m->scratch);
         if (i < m->ev_render.size() && m->ev_render[i]) cudaEventDestroy(m->ev_render[i]);
         if (i < m->ev_xchg.size() && m->ev_xchg[i]) cudaEventDestroy(m->ev_xchg[i]);
@@ -305,7 +323,7 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
     P.flags = o.flags;
     P.scale = (o.flags & B200RT_FLAG_SUM) || count == 0 ? 1.0f : (float)(1.0 / (double)count);
     P.counters = s->d_counters;
-    CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 3 * sizeof(unsigned long long), st));
+    CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), st));
     unsigned long long launches = 1;
     CUDA_TRY(cudaEventRecord(s->ev0, st));
     if (count == 0) {
@@ -341,13 +359,13 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
         stats->kernel_launches = launches;
         stats->n_devices = 1;
         if (sync_for_stats) {
-            unsigned long long c[3];
+            unsigned long long c[4];
             CUDA_TRY(cudaMemcpyAsync(c, s->d_counters, sizeof c, cudaMemcpyDeviceToHost, st));
             CUDA_TRY(cudaStreamSynchronize(st));
             float ms = 0;
             CUDA_TRY(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
             stats->kernel_ms = ms;
-            stats->rays = c[0]; stats->node_visits = c[1]; stats->prim_tests = c[2];
+            stats->rays = c[0]; stats->node_visits = c[1]; stats->prim_tests = c[2]; stats->quad_tests = c[3];
         }
     }
     return B200RT_OK;
@@ -416,13 +434,13 @@ int scene_build_host(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, S
     {
         std::vector<float4> flat(bvh.nodes.size() * 8);
         std::memcpy(flat.data(), bvh.nodes.data(), bvh.nodes.size() * sizeof(Node4));
-        rc = upload(flat, &d_nodes, &s->allocs[0], &s->alloc_bytes[0], bytes);
+        rc = upload(s, 0, flat, &d_nodes, bytes);
     }
-    if (!rc) rc = upload(sph, &s->d.spheres, &s->allocs[1], &s->alloc_bytes[1], bytes);
-    if (!rc) rc = upload(sph_meta, &s->d.sphere_meta, &s->allocs[2], &s->alloc_bytes[2], bytes);
-    if (!rc) rc = upload(quads, &s->d.quads, &s->allocs[3], &s->alloc_bytes[3], bytes);
-    if (!rc) rc = upload(quad_meta, &s->d.quad_meta, &s->allocs[4], &s->alloc_bytes[4], bytes);
-    if (!rc) rc = upload(mats, &s->d.materials, &s->allocs[5], &s->alloc_bytes[5], bytes);
+    if (!rc) rc = upload(s, 1, sph, &s->d.spheres, bytes);
+    if (!rc) rc = upload(s, 2, sph_meta, &s->d.sphere_meta, bytes);
+    if (!rc) rc = upload(s, 3, quads, &s->d.quads, bytes);
+    if (!rc) rc = upload(s, 4, quad_meta, &s->d.quad_meta, bytes);
+    if (!rc) rc = upload(s, 5, mats, &s->d.materials, bytes);
     if (!rc && cudaStreamSynchronize(0) != cudaSuccess) rc = fail(B200RT_ECUDA, "scene upload failed");
     s->d.nodes = d_nodes;
     if (rc) return rc;
@@ -448,6 +466,7 @@ int scene_build_gpu(const B200rtSceneDesc *desc, SceneImpl *s, bool *too_deep) {
     const uint32_t n_sph = (uint32_t)desc->n_spheres, n_quad = (uint32_t)desc->n_quads;
     if (n_sph > kLeafIndexMask || n_quad > kLeafIndexMask || (uint64_t)n_sph + n_quad > (1u << 29))
         return fail(B200RT_EINVAL, "too many primitives for the leaf encoding (2^26 per type)");
+    if (desc->n_materials > 0xFFFFFFFFull) return fail(B200RT_EINVAL, "too many materials");
     uint64_t bytes = 0;
     // The caller's structs go up as they are (pinned staging, pipelined); the scene's own arrays are allocated
     // straight into s->allocs so that free_scene releases them on every failure path below.
@@ -461,23 +480,47 @@ int scene_build_gpu(const B200rtSceneDesc *desc, SceneImpl *s, bool *too_deep) {
     CUDA_TRY(dev_alloc_async(&raw_quad, (size_t)n_quad * sizeof(B200rtQuad), 0));
     const size_t sizes[6] = {0, (size_t)n_sph * 2 * sizeof(double2), (size_t)n_sph * sizeof(uint2),
                              (size_t)n_quad * 8 * sizeof(double2), (size_t)n_quad * sizeof(uint2), 0};
-    for (int i = 1; i <= 4; ++i) {
-        CUDA_TRY(dev_alloc_async(&s->allocs[i], sizes[i], 0));
-        s->alloc_bytes[i] = sizes[i];
-    }
+    for (int i = 1; i <= 4; ++i) CUDA_TRY(scene_alloc(s, i, sizes[i]));
     CUDA_TRY(staged_upload(raw_sph, desc->spheres, (size_t)n_sph * sizeof(B200rtSphere), 0));
     CUDA_TRY(staged_upload(raw_quad, desc->quads, (size_t)n_quad * sizeof(B200rtQuad), 0));
     double2 *d_sph = static_cast<double2 *>(s->allocs[1]), *d_quads = static_cast<double2 *>(s->allocs[3]);
     uint2 *d_sph_meta = static_cast<uint2 *>(s->allocs[2]), *d_quad_meta = static_cast<uint2 *>(s->allocs[4]);
+    const bool trace = std::getenv("B200RT_TRACE") != nullptr;
+    if (trace) cudaStreamSynchronize(0);
+    const double t_up = now_ms();
     float4 *d_nodes = nullptr;
     uint32_t n_nodes = 0, depth = 0;
-    const cudaError_t e = build_lbvh_device(raw_sph, n_sph, raw_quad, n_quad, d_sph, d_sph_meta, d_quads, d_quad_meta, &d_nodes, &n_nodes, &depth);
+    int bad_index = 0;
+    const cudaError_t e = build_lbvh_device(raw_sph, n_sph, raw_quad, n_quad, (uint32_t)desc->n_materials, d_sph, d_sph_meta, d_quads,
+                                            d_quad_meta, &d_nodes, &n_nodes, &depth, &bad_index);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, std::string("GPU BVH build: ") + cudaGetErrorString(e)); }
-    s->allocs[0] = d_nodes;
-    s->alloc_bytes[0] = (size_t)n_nodes * sizeof(Node4);
-    if (3 * depth > 128) { *too_deep = true; return B200RT_OK; }
-    const std::vector<DeviceMaterial> mats = device_materials(desc);
-    if (int rc = upload(mats, &s->d.materials, &s->allocs[5], &s->alloc_bytes[5], bytes)) return rc;
+    if (trace) std::fprintf(stderr, "scene_build_gpu: upload %.2f ms, lbvh %.2f ms\n", t_up - t0, now_ms() - t_up);
+    if (bad_index) { dev_free(d_nodes); return fail(B200RT_EINVAL, "a sphere or quad has a material or primitive index out of range"); }
+    if (3 * depth > 128) { dev_free(d_nodes); *too_deep = true; return B200RT_OK; }
+    if (s->peer_visible) {
+        // the builder sized the node array for the worst case (n - 1 nodes) in pool memory; a multi-device scene
+        // keeps an exact-size copy in a peer-visible buffer instead (a device-to-device copy at HBM speed)
+        const cudaError_t e2 = scene_alloc(s, 0, (size_t)n_nodes * sizeof(Node4));
+        if (e2 == cudaSuccess) cudaMemcpyAsync(s->allocs[0], d_nodes, (size_t)n_nodes * sizeof(Node4), cudaMemcpyDeviceToDevice, 0);
+        dev_free(d_nodes);
+        if (e2 != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ENOMEM, "node array copy"); }
+        d_nodes = static_cast<float4 *>(s->allocs[0]);
+    } else {
+        s->allocs[0] = d_nodes;
+        s->alloc_bytes[0] = (size_t)n_nodes * sizeof(Node4);
+    }
+    {   // materials: the caller's records go up as they are and are converted (and their kinds checked) on the device
+        B200rtMaterial *raw_mat = nullptr;
+        CUDA_TRY(dev_alloc_async(&raw_mat, (size_t)desc->n_materials * sizeof(B200rtMaterial), 0));
+        struct MatGuard { B200rtMaterial *&p; ~MatGuard() { dev_free(p); } } mat_guard{raw_mat};
+        CUDA_TRY(scene_alloc(s, 5, (size_t)desc->n_materials * sizeof(DeviceMaterial)));
+        CUDA_TRY(staged_upload(raw_mat, desc->materials, (size_t)desc->n_materials * sizeof(B200rtMaterial), 0));
+        int bad_kind = 0;
+        CUDA_TRY(convert_materials_device(raw_mat, (uint32_t)desc->n_materials, static_cast<DeviceMaterial *>(s->allocs[5]), &bad_kind));
+        if (bad_kind) return fail(B200RT_EINVAL, "unknown material kind (closed set: Lambertian, Metal, Dielectric, DiffuseLight)");
+        s->d.materials = static_cast<const DeviceMaterial *>(s->allocs[5]);
+        bytes += (uint64_t)desc->n_materials * sizeof(DeviceMaterial);
+    }
     if (reinterpret_cast<uintptr_t>(d_nodes) & 127)   // trav_node_step forms plane addresses with OR / XOR on the low bits
         return fail(B200RT_ECUDA, "node array is not 128-byte aligned");
     s->d.nodes = d_nodes;
@@ -498,7 +541,7 @@ int scene_build_gpu(const B200rtSceneDesc *desc, SceneImpl *s, bool *too_deep) {
 
 // Per-scene launch state (counters, events, the bounds-check table of the debug build); `s->device` is current.
 int finish_scene_setup(SceneImpl *s) {
-    cudaError_t e = dev_alloc(&s->d_counters, 3 * sizeof(unsigned long long));
+    cudaError_t e = dev_alloc(&s->d_counters, 4 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, s->device);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&s->ev1);
@@ -520,10 +563,11 @@ int finish_scene_setup(SceneImpl *s) {
 }
 
 // Builds the acceleration structure for `desc` and makes the scene resident on device `dev`.
-int create_scene_on(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, int dev, SceneImpl **out) {
+int create_scene_on(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, int dev, bool peer_visible, SceneImpl **out) {
     *out = nullptr;
     SceneImpl *s = new SceneImpl();
     s->device = dev;
+    s->peer_visible = peer_visible;
     DeviceGuard g(dev);
     if (!g.ok) { delete s; return fail(B200RT_ECUDA, "cudaSetDevice failed"); }
     const uint64_t n_prims = desc->n_spheres + desc->n_quads;
@@ -533,16 +577,19 @@ int create_scene_on(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, in
     // tens of ms incl. the upload vs 0.8 / 1.0 s, with equal or better render rates)
     if (builder == B200RT_BUILDER_AUTO) builder = n_prims >= 65536 ? B200RT_BUILDER_GPU_LBVH : B200RT_BUILDER_HOST_SAH;
     bool built = false;
-    if (builder == B200RT_BUILDER_GPU_LBVH && n_prims >= 2) {
+    const bool gpu_build = builder == B200RT_BUILDER_GPU_LBVH && n_prims >= 2;
+    if (int rc = validate_desc(desc, !gpu_build)) { delete s; return rc; }
+    if (gpu_build) {
         bool too_deep = false;
         if (int rc = scene_build_gpu(desc, s, &too_deep)) { free_scene(s); return rc; }
         if (too_deep) {   // pathological depth: start over with the depth-capped host builder
-            for (int i = 0; i < 6; ++i) { dev_free(s->allocs[i]); s->allocs[i] = nullptr; s->alloc_bytes[i] = 0; }
+            scene_free_arrays(s);
         } else {
             built = true;
         }
     }
     if (!built) {
+        if (gpu_build) { if (int rc = validate_desc(desc, true)) { free_scene(s); return rc; } }
         if (int rc = scene_build_host(desc, opts, s)) { free_scene(s); return rc; }
     }
     s->info.n_prims = n_prims;
@@ -559,18 +606,18 @@ int replicate_scene_on(const SceneImpl *src, int dev, SceneImpl **out) {
     *out = nullptr;
     SceneImpl *s = new SceneImpl();
     s->device = dev;
+    s->peer_visible = true;
     DeviceGuard g(dev);
     if (!g.ok) { delete s; return fail(B200RT_ECUDA, "cudaSetDevice failed"); }
     for (int i = 0; i < 6; ++i) {
         if (!src->allocs[i]) continue;
-        cudaError_t e = dev_alloc_async(&s->allocs[i], src->alloc_bytes[i], 0);
+        cudaError_t e = scene_alloc(s, i, src->alloc_bytes[i]);
         if (e == cudaSuccess) e = cudaMemcpyPeerAsync(s->allocs[i], dev, src->allocs[i], src->device, src->alloc_bytes[i], 0);
         if (e != cudaSuccess) {
             cudaGetLastError();
             free_scene(s);
             return fail(e == cudaErrorMemoryAllocation ? B200RT_ENOMEM : B200RT_ECUDA, std::string("scene copy to a peer device: ") + cudaGetErrorString(e));
         }
-        s->alloc_bytes[i] = src->alloc_bytes[i];
     }
     s->d.nodes = static_cast<const float4 *>(s->allocs[0]);
     s->d.spheres = static_cast<const double2 *>(s->allocs[1]);
@@ -587,12 +634,12 @@ int replicate_scene_on(const SceneImpl *src, int dev, SceneImpl **out) {
 }
 
 void collect_stats(SceneImpl *s, B200rtStats *st) {   // after the stream that rendered has been synchronised
-    unsigned long long c[3] = {0, 0, 0};
+    unsigned long long c[4] = {0, 0, 0, 0};
     cudaMemcpy(c, s->d_counters, sizeof c, cudaMemcpyDeviceToHost);
     float ms = 0;
     if (cudaEventElapsedTime(&ms, s->ev0, s->ev1) != cudaSuccess) { cudaGetLastError(); ms = 0; }
     st->kernel_ms = ms;
-    st->rays = c[0]; st->node_visits = c[1]; st->prim_tests = c[2];
+    st->rays = c[0]; st->node_visits = c[1]; st->prim_tests = c[2]; st->quad_tests = c[3];
 }
 
 // One frame on all devices of `m` into the caller's host buffer: sample split, exchange, scale, read back.
@@ -611,10 +658,10 @@ int render_multi(MultiImpl *m, const B200rtCamera *cam, const B200rtRenderOpts *
     if (floats > m->frame_floats) {
         for (int d = 0; d < n; ++d) {
             DeviceGuard g(m->dev[d]->device);
-            dev_free(m->frame[d]); m->frame[d] = nullptr;
+            peer_buffer_release(m->dev[d]->device, m->frame[d]); m->frame[d] = nullptr;
             if (d == 0) { dev_free(m->scratch); m->scratch = nullptr; }
             m->frame_floats = 0;
-            CUDA_TRY(dev_alloc(&m->frame[d], floats * sizeof(float)));
+            CUDA_TRY(peer_buffer_acquire(m->dev[d]->device, floats * sizeof(float), reinterpret_cast<void **>(&m->frame[d])));
             if (d == 0 && !m->peers) CUDA_TRY(dev_alloc(&m->scratch, floats * sizeof(float)));
         }
         m->frame_floats = floats;
@@ -687,7 +734,7 @@ int render_multi(MultiImpl *m, const B200rtCamera *cam, const B200rtRenderOpts *
         collect_stats(m->dev[d], &st[d]);
         total.kernel_ms = std::max(total.kernel_ms, st[d].kernel_ms);
         total.paths += st[d].paths; total.rays += st[d].rays;
-        total.node_visits += st[d].node_visits; total.prim_tests += st[d].prim_tests;
+        total.node_visits += st[d].node_visits; total.prim_tests += st[d].prim_tests; total.quad_tests += st[d].quad_tests;
         total.kernel_launches += st[d].kernel_launches;
     }
     {
@@ -741,6 +788,7 @@ int b200rt_camera_init(B200rtCamera *c) {
 
 int b200rt_trim(void) {
     if (device_count_quiet() == 0) return B200RT_OK;
+    peer_buffer_trim();
     if (dev_pool_trim_all() != cudaSuccess) { cudaGetLastError(); return fail(B200RT_ECUDA, "cudaMemPoolTrimTo failed"); }
     return B200RT_OK;
 }
@@ -748,13 +796,13 @@ int b200rt_trim(void) {
 int b200rt_scene_create(const B200rtSceneDesc *desc, const B200rtBuildOpts *opts, void **scene_out) {
     if (!scene_out) return fail(B200RT_EINVAL, "scene_out is NULL");
     *scene_out = nullptr;
-    if (int rc = validate_desc(desc)) return rc;
+    if (int rc = validate_desc(desc, false)) return rc;   // per-primitive checks: in create_scene_on, by whoever builds
     if (device_count_quiet() == 0) return fail(B200RT_ENODEVICE, "no CUDA device: libb200rt has no CPU path");
     int dev = opts ? opts->device : -1;
     if (dev < 0) { if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); dev = 0; } }
     if (dev >= device_count_quiet() || dev >= kMaxDevices) return fail(B200RT_EINVAL, "device ordinal out of range");
     SceneImpl *s = nullptr;
-    if (int rc = create_scene_on(desc, opts, dev, &s)) return rc;
+    if (int rc = create_scene_on(desc, opts, dev, false, &s)) return rc;
     *scene_out = s;
     return B200RT_OK;
 }
@@ -763,7 +811,7 @@ int b200rt_scene_create_multi(const B200rtSceneDesc *desc, const B200rtBuildOpts
                               void **scene_out) {
     if (!scene_out) return fail(B200RT_EINVAL, "scene_out is NULL");
     *scene_out = nullptr;
-    if (int rc = validate_desc(desc)) return rc;
+    if (int rc = validate_desc(desc, false)) return rc;
     const int have = device_count_quiet();
     if (have == 0) return fail(B200RT_ENODEVICE, "no CUDA device: libb200rt has no CPU path");
     if (n_devices < 1 || n_devices > kMaxPeers) return fail(B200RT_EINVAL, "device count must be 1 .. 16");
@@ -776,7 +824,7 @@ int b200rt_scene_create_multi(const B200rtSceneDesc *desc, const B200rtBuildOpts
     }
     if (n_devices == 1) {
         SceneImpl *s = nullptr;
-        if (int rc = create_scene_on(desc, opts, devs[0], &s)) return rc;
+        if (int rc = create_scene_on(desc, opts, devs[0], false, &s)) return rc;
         *scene_out = s;
         return B200RT_OK;
     }
@@ -786,7 +834,6 @@ int b200rt_scene_create_multi(const B200rtSceneDesc *desc, const B200rtBuildOpts
     m->ev_render.assign(n_devices, nullptr);
     m->ev_xchg.assign(n_devices, nullptr);
     m->frame.assign(n_devices, nullptr);
-    if (int rc = create_scene_on(desc, opts, devs[0], &m->dev[0])) { free_multi(m); return rc; }
     const double t0 = now_ms();
     // Peer mapping: every device must be able to dereference every other device's pool memory for the fused
     // exchange; cudaMemcpyPeerAsync (the scene copies) works either way but goes over NVLink only between peers.
@@ -803,10 +850,13 @@ int b200rt_scene_create_multi(const B200rtSceneDesc *desc, const B200rtBuildOpts
             cudaGetLastError();
         }
     }
-    if (all_peers)
-        for (int i = 0; i < n_devices; ++i)
-            if (dev_pool_allow_peers(devs[i], devs.data(), n_devices) != cudaSuccess) { cudaGetLastError(); all_peers = false; }
+    // B200RT_MULTI_NO_PEER=1 forces the exchange without peer mapping (copies + accumulate on devices[0]); tests use it
+    // to cover that path on NVLink boxes.  The frames peers dereference are cudaMalloc memory (devmem.h), which
+    // cudaDeviceEnablePeerAccess maps; the pools' memory is only ever the source / target of peer COPIES.
+    if (const char *np = std::getenv("B200RT_MULTI_NO_PEER")) if (np[0] == '1') all_peers = false;
     m->peers = all_peers;
+    if (int rc = create_scene_on(desc, opts, devs[0], true, &m->dev[0])) { free_multi(m); return rc; }
+    const double t_built = now_ms();
     for (int i = 1; i < n_devices; ++i)   // all copies are in flight together, one per destination device
         if (int rc = replicate_scene_on(m->dev[0], devs[i], &m->dev[i])) { free_multi(m); return rc; }
     for (int i = 0; i < n_devices; ++i) {
@@ -817,7 +867,8 @@ int b200rt_scene_create_multi(const B200rtSceneDesc *desc, const B200rtBuildOpts
         if (e == cudaSuccess) e = cudaDeviceSynchronize();   // this device's copy of the scene has landed
         if (e != cudaSuccess) { cudaGetLastError(); free_multi(m); return fail(B200RT_ECUDA, std::string("multi-device setup: ") + cudaGetErrorString(e)); }
     }
-    m->replicate_ms = now_ms() - t0;
+    m->replicate_ms = now_ms() - t_built;
+    if (std::getenv("B200RT_TRACE")) std::fprintf(stderr, "scene_create_multi: peer setup + build %.2f ms, replicate %.2f ms\n", t_built - t0, m->replicate_ms);
     *scene_out = m;
     return B200RT_OK;
 }
@@ -983,7 +1034,7 @@ int b200rt_debug_lane_accounting(void *scene, const B200rtCamera *cam, const B20
     CUDA_TRY(dev_alloc(&d_frame, (size_t)cam->image_w * cam->image_h * 3 * sizeof(float)));
     cudaError_t e = dev_alloc(&d_acc, 16 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMemsetAsync(d_acc, 0, 16 * sizeof(unsigned long long), 0);
-    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_counters, 0, 3 * sizeof(unsigned long long), 0);
+    if (e == cudaSuccess) e = cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), 0);
     P.scene = s->d; P.seed = o.seed; P.sample_begin = (uint32_t)o.sample_offset; P.sample_count = (uint32_t)count;
     P.out = d_frame; P.flags = 0; P.scale = 1.0f; P.counters = s->d_counters;
     if (e == cudaSuccess) e = launch_path_lanes(s->stack, P, d_acc, 0);
@@ -1049,8 +1100,10 @@ int b200rt_render_scene_multi(const B200rtSceneDesc *desc, const B200rtCamera *c
     }
     void *scene = nullptr;
     if (int rc = b200rt_scene_create_multi(desc, bopts, devices, n_devices, &scene)) return rc;
+    const double t1 = now_ms();
     B200rtStats local{};
     int rc = b200rt_render(scene, cam, opts, out_rgb, &local);
+    const double t2 = now_ms();
     if (!rc) {
         const SceneImpl *s = root_scene(scene);
         local.h2d_ms = s->info.upload_ms;
@@ -1060,6 +1113,9 @@ int b200rt_render_scene_multi(const B200rtSceneDesc *desc, const B200rtCamera *c
     }
     b200rt_scene_destroy(scene);
     local.total_ms = now_ms() - t0;
+    if (std::getenv("B200RT_TRACE"))
+        std::fprintf(stderr, "b200rt_render_scene_multi: create %.2f ms (build %.2f, replicate %.2f), render %.2f ms (kernel %.2f, exchange %.3f, d2h %.2f), destroy %.2f ms\n",
+                     t1 - t0, local.build_ms, local.replicate_ms, t2 - t1, local.kernel_ms, local.exchange_ms, local.d2h_ms, now_ms() - t2);
     if (!rc && stats) *stats = local;
     return rc;
 }

@@ -6,6 +6,7 @@
 #include <cstring>
 #include <memory>
 #include <mutex>
+#include <vector>
 
 #include "thread_pool.h"
 
@@ -42,6 +43,17 @@ cudaError_t device_pool(int dev, cudaMemPool_t *out) {
     }
     *out = P.pool[dev];
     return cudaSuccess;
+}
+
+// ---- peer-shared frames --------------------------------------------------------------------
+struct SharedFrame { void *p; size_t bytes; bool busy; };
+struct SharedFrames {
+    std::mutex mu;
+    std::vector<SharedFrame> per_dev[kMaxDevices];
+};
+SharedFrames &shared_frames() {
+    static SharedFrames f;
+    return f;
 }
 
 // ---- pinned staging -------------------------------------------------------------------------
@@ -118,23 +130,6 @@ void dev_free_on(void *p, cudaStream_t st) {
     if (p) cudaFreeAsync(p, st);
 }
 
-cudaError_t dev_pool_allow_peers(int dev, const int *peers, int n_peers) {
-    cudaMemPool_t pool;
-    cudaError_t e = device_pool(dev, &pool);
-    if (e != cudaSuccess) return e;
-    cudaMemAccessDesc desc[kMaxDevices];
-    int n = 0;
-    for (int i = 0; i < n_peers && n < kMaxDevices; ++i) {
-        if (peers[i] == dev) continue;
-        desc[n].location.type = cudaMemLocationTypeDevice;
-        desc[n].location.id = peers[i];
-        desc[n].flags = cudaMemAccessFlagsProtReadWrite;
-        ++n;
-    }
-    if (n == 0) return cudaSuccess;
-    return cudaMemPoolSetAccess(pool, desc, n);
-}
-
 cudaError_t dev_pool_trim_all() {
     DevicePools &P = pools();
     std::lock_guard<std::mutex> lk(P.mu);
@@ -145,6 +140,57 @@ cudaError_t dev_pool_trim_all() {
             if (e != cudaSuccess && first == cudaSuccess) first = e;
         }
     return first;
+}
+
+cudaError_t peer_buffer_acquire(int dev, size_t bytes, void **out) {
+    if (dev < 0 || dev >= kMaxDevices) return cudaErrorInvalidDevice;
+    SharedFrames &F = shared_frames();
+    std::lock_guard<std::mutex> lk(F.mu);
+    std::vector<SharedFrame> &v = F.per_dev[dev];
+    int best = -1;
+    for (int i = 0; i < (int)v.size(); ++i)
+        if (!v[i].busy && v[i].bytes >= bytes && v[i].bytes <= 2 * bytes + (1u << 20) && (best < 0 || v[i].bytes < v[best].bytes)) best = i;
+    if (best < 0) {
+        void *p = nullptr;
+        cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+        if (e == cudaErrorMemoryAllocation) {   // make room: drop every idle buffer of this device, then retry once
+            cudaGetLastError();
+            for (int i = (int)v.size() - 1; i >= 0; --i)
+                if (!v[i].busy) { cudaFree(v[i].p); v.erase(v.begin() + i); }
+            e = cudaMalloc(&p, bytes ? bytes : 1);
+        }
+        if (e != cudaSuccess) return e;
+        v.push_back(SharedFrame{p, bytes, false});
+        best = (int)v.size() - 1;
+    }
+    v[best].busy = true;
+    *out = v[best].p;
+    return cudaSuccess;
+}
+
+void peer_buffer_release(int dev, void *p) {
+    if (!p || dev < 0 || dev >= kMaxDevices) return;
+    SharedFrames &F = shared_frames();
+    std::lock_guard<std::mutex> lk(F.mu);
+    for (SharedFrame &f : F.per_dev[dev])
+        if (f.p == p) f.busy = false;
+}
+
+void peer_buffer_trim() {
+    SharedFrames &F = shared_frames();
+    std::lock_guard<std::mutex> lk(F.mu);
+    int prev = -1;
+    cudaGetDevice(&prev);
+    for (int d = 0; d < kMaxDevices; ++d) {
+        std::vector<SharedFrame> &v = F.per_dev[d];
+        for (int i = (int)v.size() - 1; i >= 0; --i)
+            if (!v[i].busy) {
+                cudaSetDevice(d);
+                cudaFree(v[i].p);
+                v.erase(v.begin() + i);
+            }
+    }
+    if (prev >= 0) cudaSetDevice(prev);
 }
 
 cudaError_t staged_upload(void *dst_device, const void *src_host, size_t bytes, cudaStream_t st) {

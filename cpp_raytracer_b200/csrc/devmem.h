@@ -27,10 +27,16 @@ template <typename T>
 cudaError_t dev_alloc_async(T **p, size_t bytes, cudaStream_t st) { return dev_alloc_async(reinterpret_cast<void **>(p), bytes, st); }
 void dev_free(void *p);                        // cudaFreeAsync on the legacy default stream of the CURRENT device
 void dev_free_on(void *p, cudaStream_t st);
-// Makes the pool of `dev` readable and writable from every device in `peers` (needed before a kernel on a peer
-// dereferences pool memory; cudaMemcpyPeerAsync does not need it).
-cudaError_t dev_pool_allow_peers(int dev, const int *peers, int n_peers);
 cudaError_t dev_pool_trim_all();
+
+// Buffers that OTHER devices touch -- the frames the fused multi-GPU exchange dereferences, and the scene arrays that
+// are copied device to device -- are plain cudaMalloc memory, which cudaDeviceEnablePeerAccess maps into every peer
+// (stream-ordered pool memory is not mapped unless the whole pool is opened with cudaMemPoolSetAccess, and then peer
+// copies of it fall back to staging otherwise).  They are cached per device across calls, because the one-call render
+// entry creates and destroys its scene every frame; b200rt_trim() frees the idle ones.  `dev` must be the current device.
+cudaError_t peer_buffer_acquire(int dev, size_t bytes, void **out);
+void peer_buffer_release(int dev, void *p);
+void peer_buffer_trim();
 
 // Pageable host memory -> device, pipelined through pinned staging chunks; returns after the LAST chunk has been
 // enqueued on `st` (the host source has been fully read by then; the device copy completes in stream order).

@@ -138,12 +138,13 @@ __device__ __forceinline__ void write_pixel_and_counters(const RenderParams &P, 
     for (int off = 16; off; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
     if ((threadIdx.x & 31) == 0 && rays) atomicAdd(&P.counters[0], rays);
     if (count) {
-        unsigned long long a = ctr.nodes, b = ctr.prims;
+        unsigned long long a = ctr.nodes, b = ctr.prims, c = ctr.quads;
         for (int off = 16; off; off >>= 1) {
             a += __shfl_down_sync(0xffffffffu, a, off);
             b += __shfl_down_sync(0xffffffffu, b, off);
+            c += __shfl_down_sync(0xffffffffu, c, off);
         }
-        if ((threadIdx.x & 31) == 0) { atomicAdd(&P.counters[1], a); atomicAdd(&P.counters[2], b); }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&P.counters[1], a); atomicAdd(&P.counters[2], b); atomicAdd(&P.counters[3], c); }
     }
 }
 

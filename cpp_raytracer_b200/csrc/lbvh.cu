@@ -6,7 +6,7 @@
 // even the parallel host SAH builder (bvh_builder.cpp, ~0.8 s) costs more than the render at 8 GPUs.
 //
 // Pipeline, all device-side (the host only uploads the caller's flat arrays as they are):
-//   1. prim_setup      primitive bounds exactly as the reference's constructors compute them
+//   1. prim_setup      index validation of the description; primitive bounds exactly as the reference's constructors compute them
 //                      (sphere.h:112-123, parallelogram.h:281-295) in double, rounded outward to FP32;
 //                      centroid bounds by warp shuffle + ordered-int atomics
 //   2. morton_codes    63-bit Morton code of the centroid (21 bits per axis)
@@ -46,13 +46,17 @@ struct PrimBoxes {
 };
 
 __global__ void prim_setup(const B200rtSphere *sph, uint32_t n_sph, const B200rtQuad *quads, uint32_t n_quad, PrimBoxes B,
-                           int *cbounds /* [6]: ordered-int min xyz, max xyz */) {
+                           int *cbounds /* [6]: ordered-int min xyz, max xyz; [6]: bad-index flag */, uint32_t n_materials) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t n = n_sph + n_quad;
     float c[3] = {0.f, 0.f, 0.f};
     const bool valid = i < n;
     if (valid) {
         double lo[3], hi[3];
+        // the scene description's index checks (material / canonical primitive index in range) happen here for the
+        // multi-million-primitive scenes instead of in a serial host loop over the caller's arrays
+        const uint32_t mat = i < n_sph ? sph[i].mat : quads[i - n_sph].mat, prim = i < n_sph ? sph[i].prim : quads[i - n_sph].prim;
+        if (mat >= n_materials || prim >= n) cbounds[6] = 1;
         if (i < n_sph) {                                   // sphere.h:112-123
             const B200rtSphere s = sph[i];
             for (int a = 0; a < 3; ++a) {
@@ -294,6 +298,23 @@ __global__ void reorder_prims(const B200rtSphere *sph, uint32_t n_sph, const B20
     }
 }
 
+// B200rtMaterial (the caller's 40-byte records) -> DeviceMaterial, as api.cu's device_materials() does on the host for
+// small scenes: lights pre-multiplied by their intensity (material.h:261-263), metal fuzz clamped to 1
+// (material.h:150-151).  The reference's big scenes carry one material PER PRIMITIVE (millions), so this runs here.
+__global__ void convert_materials(const B200rtMaterial *__restrict__ raw, uint32_t n, DeviceMaterial *__restrict__ out, int *bad_kind) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const B200rtMaterial m = raw[i];
+    if (m.kind > B200RT_MAT_LIGHT) *bad_kind = 1;
+    DeviceMaterial dm;
+    const double k = m.kind == B200RT_MAT_LIGHT ? m.param : 1.0;
+    dm.r = (float)(k * m.rgb[0]); dm.g = (float)(k * m.rgb[1]); dm.b = (float)(k * m.rgb[2]);
+    dm.kind = m.kind;
+    dm.param = m.kind == B200RT_MAT_METAL ? fmin(m.param, 1.0) : m.param;
+    dm.pad = 0.0;
+    out[i] = dm;
+}
+
 template <typename T>
 cudaError_t tmp_alloc(std::vector<void *> &owned, T **p, size_t count) {
     void *q = nullptr;
@@ -306,13 +327,29 @@ cudaError_t tmp_alloc(std::vector<void *> &owned, T **p, size_t count) {
 
 }  // namespace
 
+cudaError_t convert_materials_device(const B200rtMaterial *d_raw, uint32_t n, DeviceMaterial *d_out, int *bad_kind_out) {
+    *bad_kind_out = 0;
+    if (n == 0) return cudaSuccess;
+    int *flag = nullptr;
+    cudaError_t e = dev_alloc_async(&flag, sizeof(int), 0);
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(flag, 0, sizeof(int), 0);
+    if (e == cudaSuccess) {
+        convert_materials<<<(n + 255) / 256, 256>>>(d_raw, n, d_out, flag);
+        e = cudaMemcpyAsync(bad_kind_out, flag, sizeof(int), cudaMemcpyDeviceToHost, 0);
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(0);
+    dev_free(flag);
+    return e;
+}
+
 // Builds the scene's device arrays on the GPU.  d_sph / d_quads are the caller's flat structs already
 // on the device.  Outputs (allocated by the caller with the sizes known up front): leaf-ordered
 // sphere / quad / meta arrays; the Node4 array is allocated here (its size is only known at the end)
 // with cudaMallocAsync and handed back through nodes_out.
 cudaError_t build_lbvh_device(const B200rtSphere *d_sph, uint32_t n_sph, const B200rtQuad *d_quads, uint32_t n_quad,
-                              double2 *out_sph, uint2 *out_sph_meta, double2 *out_quads, uint2 *out_quad_meta,
-                              float4 **nodes_out, uint32_t *n_nodes_out, uint32_t *depth_out) {
+                              uint32_t n_materials, double2 *out_sph, uint2 *out_sph_meta, double2 *out_quads, uint2 *out_quad_meta,
+                              float4 **nodes_out, uint32_t *n_nodes_out, uint32_t *depth_out, int *bad_index_out) {
     const uint32_t n = n_sph + n_quad;
     // Encoding limits: a leaf reference holds a 26-bit index into its per-type array (bvh_builder.h), and the radix
     // tree's index arithmetic ((n - 1) + ~child, lmax * d) must stay inside int.  The host builder rejects the same
@@ -330,10 +367,12 @@ cudaError_t build_lbvh_device(const B200rtSphere *d_sph, uint32_t n_sph, const B
     LB(tmp_alloc(owned, &pb.hix, n)); LB(tmp_alloc(owned, &pb.hiy, n)); LB(tmp_alloc(owned, &pb.hiz, n));
     LB(tmp_alloc(owned, &pb.cx, n)); LB(tmp_alloc(owned, &pb.cy, n)); LB(tmp_alloc(owned, &pb.cz, n));
     int *cbounds;
-    LB(tmp_alloc(owned, &cbounds, 6));
-    const int init[6] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000};
+    LB(tmp_alloc(owned, &cbounds, 7));
+    const int init[7] = {0x7fffffff, 0x7fffffff, 0x7fffffff, (int)0x80000000, (int)0x80000000, (int)0x80000000, 0};
     LB(cudaMemcpyAsync(cbounds, init, sizeof init, cudaMemcpyHostToDevice, 0));
-    prim_setup<<<gn, B>>>(d_sph, n_sph, d_quads, n_quad, pb, cbounds);
+    prim_setup<<<gn, B>>>(d_sph, n_sph, d_quads, n_quad, pb, cbounds, n_materials);
+    int bad_index = 0;
+    LB(cudaMemcpyAsync(&bad_index, cbounds + 6, sizeof(int), cudaMemcpyDeviceToHost, 0));   // read at the first sync below
     unsigned long long *keys, *keys_alt;
     uint32_t *vals, *vals_alt;
     LB(tmp_alloc(owned, &keys, n)); LB(tmp_alloc(owned, &keys_alt, n));
@@ -393,6 +432,7 @@ cudaError_t build_lbvh_device(const B200rtSphere *d_sph, uint32_t n_sph, const B
     LB(cudaStreamSynchronize(0));
     LB(cudaGetLastError());
     cleanup();
+    *bad_index_out = bad_index;
     *nodes_out = reinterpret_cast<float4 *>(nodes4);
     *n_nodes_out = n_nodes;
     *depth_out = depth;

@@ -63,7 +63,7 @@ struct Hit {
 };
 
 struct TraversalCounters {
-    unsigned long long nodes = 0, prims = 0;
+    unsigned long long nodes = 0, prims = 0, quads = 0;   // node visits, primitive tests (all), of which quads
 };
 
 __device__ __forceinline__ uint32_t canonical_prim(const DeviceScene &S, uint32_t ref) {
@@ -335,8 +335,9 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene &S, double ox, doub
                 trav_node_step(S, T, stack);
             }
             while (trav_at_leaf(T)) {
+                const bool is_quad = T.cur & kQuadFlagD;
                 const uint32_t c = trav_leaf_step(S, T, stack);
-                if (COUNT) ctr->prims += c;
+                if (COUNT) { ctr->prims += c; if (is_quad) ctr->quads += c; }
             }
         }
         return T.best;
@@ -346,8 +347,9 @@ __device__ __forceinline__ Hit closest_hit(const DeviceScene &S, double ox, doub
             if (COUNT) ctr->nodes++;
             trav_node_step(S, T, stack);
         } else {
+            const bool is_quad = T.cur & kQuadFlagD;
             const uint32_t c = trav_leaf_step(S, T, stack);
-            if (COUNT) ctr->prims += c;
+            if (COUNT) { ctr->prims += c; if (is_quad) ctr->quads += c; }
         }
     }
     return T.best;

@@ -142,8 +142,9 @@ __global__ void __launch_bounds__(kPathBlock, kPathMinBlocks) wf_trace(const __g
                 if (COUNT) ctr.nodes++;
                 trav_node_step(P.scene, T, stack);
             } else {
+                const bool is_quad = T.cur & kQuadFlagD;
                 const uint32_t c = trav_leaf_step(P.scene, T, stack);
-                if (COUNT) ctr.prims += c;
+                if (COUNT) { ctr.prims += c; if (is_quad) ctr.quads += c; }
             }
             if (trav_done(T)) { have = false; parked = true; ++rays; }
         }
@@ -152,9 +153,11 @@ __global__ void __launch_bounds__(kPathBlock, kPathMinBlocks) wf_trace(const __g
     for (int off = 16; off; off >>= 1) r += __shfl_down_sync(0xffffffffu, r, off);
     if (lane == 0 && r) atomicAdd(&P.counters[0], r);
     if (COUNT) {
-        unsigned long long a = ctr.nodes, b = ctr.prims;
-        for (int off = 16; off; off >>= 1) { a += __shfl_down_sync(0xffffffffu, a, off); b += __shfl_down_sync(0xffffffffu, b, off); }
-        if (lane == 0) { atomicAdd(&P.counters[1], a); atomicAdd(&P.counters[2], b); }
+        unsigned long long a = ctr.nodes, b = ctr.prims, q = ctr.quads;
+        for (int off = 16; off; off >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, off); b += __shfl_down_sync(0xffffffffu, b, off); q += __shfl_down_sync(0xffffffffu, q, off);
+        }
+        if (lane == 0) { atomicAdd(&P.counters[1], a); atomicAdd(&P.counters[2], b); atomicAdd(&P.counters[3], q); }
     }
 }
 

@@ -145,6 +145,7 @@ typedef struct B200rtStats {
     double exchange_ms;        /* multi-GPU: summing the per-device frames onto the first device + scaling */
     uint32_t n_devices;        /* devices that rendered */
     uint32_t peer_exchange;    /* 1: fused peer-memory kernel (one launch per device); 0: copies + accumulate on the root */
+    uint64_t quad_tests;       /* with B200RT_FLAG_COUNTERS: how many of prim_tests were parallelogram tests (the rest: spheres) */
 } B200rtStats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

@@ -81,6 +81,16 @@ def test_multi_gpu_frame_equals_single_gpu_frame(golden, name):
         assert np.array_equal(got, again)                                       # deterministic
         # same paths, same per-sample radiance; only the FP32 order of the per-device partial sums differs
         assert np.allclose(got, want, rtol=2e-5, atol=1e-6), (name, devs, float(np.abs(got - want).max()))
+    # the exchange without peer mapping (copies + accumulate on devices[0]) adds in the same order: the same bits
+    with rt.DeviceSceneHandle(scene, devices=list(range(n))) as multi:
+        peer_frame, sp = multi.render(cam, seed=21)
+    os.environ["B200RT_MULTI_NO_PEER"] = "1"
+    try:
+        with rt.DeviceSceneHandle(scene, devices=list(range(n))) as multi:
+            copy_frame, sc = multi.render(cam, seed=21)
+    finally:
+        del os.environ["B200RT_MULTI_NO_PEER"]
+    assert sc["peer_exchange"] == 0 and np.array_equal(peer_frame, copy_frame)
     # spp smaller than the device count: some devices get an empty share
     cam2 = rt.camera_with(scene.camera, image_w=64, image_h=40, spp=1)
     with rt.DeviceSceneHandle(scene, device=0) as one:
