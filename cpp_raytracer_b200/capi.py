@@ -32,7 +32,7 @@ assert MATERIAL_DTYPE.itemsize == 40 and SPHERE_DTYPE.itemsize == 40 and QUAD_DT
 
 MAT_LAMBERTIAN, MAT_METAL, MAT_DIELECTRIC, MAT_LIGHT = 0, 1, 2, 3
 VARIANT_MEGAKERNEL, VARIANT_WAVEFRONT = 0, 1
-FLAG_SUM, FLAG_ACCUMULATE, FLAG_COUNTERS, FLAG_EXACT_COUNT = 1, 2, 4, 8
+FLAG_SUM, FLAG_ACCUMULATE, FLAG_COUNTERS, FLAG_EXACT_COUNT, FLAG_THREAD_PIXELS = 1, 2, 4, 8, 16
 BUILDER_AUTO, BUILDER_HOST_SAH, BUILDER_GPU_LBVH = 0, 1, 2
 OK, EINVAL, ENODEVICE, ECUDA, ENOMEM, EINTERNAL = 0, -1, -2, -3, -4, -5
 
@@ -266,10 +266,10 @@ class DeviceSceneHandle:
         _check(lib().b200rt_debug_bounds(self._h, out.ctypes.data))
         return out
 
-    def lane_accounting(self, cam: np.ndarray, seed: int = 0xB200, sample_offset: int = 0, sample_count: int = 0) -> np.ndarray:
+    def lane_accounting(self, cam: np.ndarray, seed: int = 0xB200, sample_offset: int = 0, sample_count: int = 0, flags: int = 0) -> np.ndarray:
         """Per-warp lane accounting of the default kernel's schedule (b200rt_debug_lane_accounting): 16 counters."""
         cam = np.ascontiguousarray(cam, dtype=CAMERA_DTYPE).reshape(1)
-        opts = RenderOpts(seed, sample_offset, sample_count, 0, 0)
+        opts = RenderOpts(seed, sample_offset, sample_count, 0, flags)
         out = np.zeros(16, dtype=np.uint64)
         _check(lib().b200rt_debug_lane_accounting(self._h, cam.ctypes.data, C.byref(opts), out.ctypes.data))
         return out

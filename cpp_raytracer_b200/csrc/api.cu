@@ -350,7 +350,16 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
         CUDA_TRY(run_wavefront(s->stack, P, W, (o.flags & B200RT_FLAG_COUNTERS) != 0, st, s->sm_count, &launches));
         CUDA_TRY(cudaEventRecord(s->ev_pool, st));
     } else {
-        CUDA_TRY(launch_path_megakernel(s->stack, P, (o.flags & B200RT_FLAG_COUNTERS) != 0, s->info.tree_depth <= 3, st));
+        // the tile work pool counts (pixel, sample) items in 32 bits: more than 2^24 samples per pixel go in several launches
+        launches = 0;
+        for (uint64_t done = 0; done < count; done += kMaxSamplesPerLaunch) {
+            RenderParams Q = P;
+            Q.sample_begin = (uint32_t)(o.sample_offset + done);
+            Q.sample_count = (uint32_t)std::min<uint64_t>(kMaxSamplesPerLaunch, count - done);
+            if (done) Q.flags |= kRenderAccumulate;
+            CUDA_TRY(launch_path_megakernel(s->stack, Q, (o.flags & B200RT_FLAG_COUNTERS) != 0, s->info.tree_depth <= 3, st));
+            ++launches;
+        }
     }
     CUDA_TRY(cudaEventRecord(s->ev1, st));
     if (stats) {
@@ -1036,7 +1045,7 @@ int b200rt_debug_lane_accounting(void *scene, const B200rtCamera *cam, const B20
     if (e == cudaSuccess) e = cudaMemsetAsync(d_acc, 0, 16 * sizeof(unsigned long long), 0);
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), 0);
     P.scene = s->d; P.seed = o.seed; P.sample_begin = (uint32_t)o.sample_offset; P.sample_count = (uint32_t)count;
-    P.out = d_frame; P.flags = 0; P.scale = 1.0f; P.counters = s->d_counters;
+    P.out = d_frame; P.flags = o.flags & B200RT_FLAG_THREAD_PIXELS; P.scale = 1.0f; P.counters = s->d_counters;
     if (e == cudaSuccess) e = launch_path_lanes(s->stack, P, d_acc, 0);
     if (e == cudaSuccess) e = cudaMemcpy(counters_out, d_acc, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaStreamSynchronize(0);

@@ -189,8 +189,151 @@ __device__ __forceinline__ bool shade_and_advance(const RenderParams &P, const P
 }
 
 // ------------------------------------------------------------------------------------------
-// path_megakernel (variant 0, default): every lane runs traverse-then-shade in a loop and starts
-// its next sample as soon as a path ends.  64 registers (16 blocks = 32 warps per SM) measured
+// Tile work pool.  A block owns an 8 x 8 pixel tile but its THREADS do not own pixels: the tile's (pixel, sample) items
+// -- sample-major, so that the lanes of a warp work on neighbouring pixels of the same sample at any time -- are handed
+// out through a shared-memory counter, and a lane whose path ends takes the next item whatever pixel it belongs to.
+// With thread-owns-pixel a lane on a cheap pixel (sky: one ray per path) ran out of samples long before its neighbours
+// on glass (five rays per path) and idled for the rest of the warp's life: 12-22 % of all lane-slots of the node and
+// leaf steps (profiles/r2_lane_accounting.md).
+//   Radiance is summed per pixel in shared memory as 64-bit FIXED POINT (2^-30 units) with integer atomics: integer
+// addition is associative, so the sum -- and with it the image -- is bit-deterministic and does not depend on which
+// lane rendered which sample, in which order.  One contribution per path (emission at a light, or the background on a
+// miss), so three atomics per path at most.  Resolution 9.3e-10, range +-8.6e9 per pixel per launch.
+struct TilePool {
+    unsigned int next;                 // next (pixel, sample) item of this tile
+    long long acc[kPathBlock * 3];     // per tile pixel: sum of radiance x 2^30
+};
+constexpr float kFixScale = 1073741824.0f;            // 2^30
+constexpr double kFixInv = 1.0 / 1073741824.0;
+
+struct TileMap {
+    uint32_t x0, y0, vw, n_valid;      // tile origin, valid width, valid pixel count (edge tiles are ragged)
+};
+__device__ __forceinline__ TileMap map_tile(const CameraParams &C) {
+    const uint32_t tiles_x = (C.w + 7u) >> 3;
+    const uint32_t tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+    TileMap t;
+    t.x0 = tile_x * 8u;
+    t.y0 = tile_y * (uint32_t)kPathTileH;
+    t.vw = min(8u, C.w - t.x0);
+    t.n_valid = t.vw * min((uint32_t)kPathTileH, C.h - t.y0);
+    return t;
+}
+
+struct PoolLane {
+    PathState p;
+    Ray ray;
+    uint32_t pixel = 0, lp = 0, s = 0, bounce = 0;    // image pixel index, pixel within the tile, sample, bounce
+    bool has_path = false;
+    uint32_t rays = 0;
+};
+
+__device__ __forceinline__ void pool_contribute(TilePool &tp, uint32_t lp, float r, float g, float b) {
+    if (r != 0.0f) atomicAdd(reinterpret_cast<unsigned long long *>(&tp.acc[lp * 3 + 0]), (unsigned long long)__float2ll_rn(r * kFixScale));
+    if (g != 0.0f) atomicAdd(reinterpret_cast<unsigned long long *>(&tp.acc[lp * 3 + 1]), (unsigned long long)__float2ll_rn(g * kFixScale));
+    if (b != 0.0f) atomicAdd(reinterpret_cast<unsigned long long *>(&tp.acc[lp * 3 + 2]), (unsigned long long)__float2ll_rn(b * kFixScale));
+}
+
+// shade_and_advance with the tile pool: same path semantics, same Philox keys (pixel, sample, bounce).
+__device__ __forceinline__ bool pool_shade_and_advance(const RenderParams &P, const TileMap &tm, TilePool &tp, uint32_t total_items,
+                                                       const Hit &best, PoolLane &L) {
+    const CameraParams &C = P.cam;
+    const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
+    if (L.has_path) {
+        ++L.rays;
+        bool cont;
+        float er = 0.0f, eg = 0.0f, eb = 0.0f;
+        if (best.ref == kNoHit) {
+            er = L.p.tr * C.background[0]; eg = L.p.tg * C.background[1]; eb = L.p.tb * C.background[2];
+            cont = false;   // camera.h:248
+        } else {
+            const Philox4 rnd = philox4x32_10(L.pixel, P.sample_begin + L.s, L.bounce + 1u, 0u, k0, k1);
+            cont = shade_hit(P.scene, best, rnd, L.ray, L.p, er, eg, eb);
+            // ray_color(scattered, depth_left - 1): contributes nothing once depth_left hits 0 (camera.h:211-213)
+            if (cont && ++L.bounce == C.max_depth) cont = false;
+        }
+        pool_contribute(tp, L.lp, er, eg, eb);
+        if (!cont) L.has_path = false;
+    }
+    if (!L.has_path) {
+        const uint32_t item = atomicAdd(&tp.next, 1u);
+        if (item >= total_items) return false;
+        if (tm.n_valid == (uint32_t)kPathBlock) { L.s = item / (uint32_t)kPathBlock; L.lp = item % (uint32_t)kPathBlock; }
+        else { L.s = item / tm.n_valid; L.lp = item - L.s * tm.n_valid; }
+        const uint32_t lx = tm.vw == 8u ? (L.lp & 7u) : L.lp % tm.vw, ly = tm.vw == 8u ? (L.lp >> 3) : L.lp / tm.vw;
+        const uint32_t px = tm.x0 + lx, py = tm.y0 + ly;
+        L.pixel = py * C.w + px;
+        const Philox4 rnd = philox4x32_10(L.pixel, P.sample_begin + L.s, 0u, 0u, k0, k1);
+        camera_ray(C, px, py, rnd, L.ray, L.p);
+        L.bounce = 0;
+        L.has_path = true;
+    }
+    return true;
+}
+
+__device__ __forceinline__ void pool_init(TilePool &tp) {
+    if (threadIdx.x == 0) tp.next = 0u;
+    for (int i = threadIdx.x; i < kPathBlock * 3; i += kPathBlock) tp.acc[i] = 0;
+    __syncthreads();
+}
+
+// After the block's last path: thread t writes tile pixel t.
+__device__ __forceinline__ void pool_write_tile(const RenderParams &P, const TileMap &tm, TilePool &tp) {
+    __syncthreads();
+    const uint32_t lp = threadIdx.x;
+    if (lp < tm.n_valid) {
+        const uint32_t px = tm.x0 + lp % tm.vw, py = tm.y0 + lp / tm.vw;
+        const uint32_t pixel = py * P.cam.w + px;
+        if (B200RT_CHECK(P.scene, pixel < P.cam.w * P.cam.h, 3)) {
+            const float sum_r = (float)((double)tp.acc[lp * 3 + 0] * kFixInv), sum_g = (float)((double)tp.acc[lp * 3 + 1] * kFixInv),
+                        sum_b = (float)((double)tp.acc[lp * 3 + 2] * kFixInv);
+            float *o = P.out + (size_t)pixel * 3;
+            const float k = P.scale;
+            if (P.flags & kRenderAccumulate) { o[0] += sum_r * k; o[1] += sum_g * k; o[2] += sum_b * k; }
+            else { o[0] = sum_r * k; o[1] = sum_g * k; o[2] = sum_b * k; }
+        }
+    }
+}
+
+__device__ __forceinline__ void write_counters(const RenderParams &P, uint32_t lane_rays, bool count, const TraversalCounters &ctr) {
+    unsigned long long rays = lane_rays;
+    for (int off = 16; off; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
+    if ((threadIdx.x & 31) == 0 && rays) atomicAdd(&P.counters[0], rays);
+    if (count) {
+        unsigned long long a = ctr.nodes, b = ctr.prims, c = ctr.quads;
+        for (int off = 16; off; off >>= 1) {
+            a += __shfl_down_sync(0xffffffffu, a, off);
+            b += __shfl_down_sync(0xffffffffu, b, off);
+            c += __shfl_down_sync(0xffffffffu, c, off);
+        }
+        if ((threadIdx.x & 31) == 0) { atomicAdd(&P.counters[1], a); atomicAdd(&P.counters[2], b); atomicAdd(&P.counters[3], c); }
+    }
+}
+
+// path_megakernel_pool (variant 0, default): every lane runs traverse-then-shade in a loop and takes the tile's next
+// (pixel, sample) item as soon as its path ends.
+template <int STACK, bool COUNT, bool SHALLOW = false, int MINB = kPathMinBlocks>
+__global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel_pool(const __grid_constant__ RenderParams P) {
+    __shared__ TilePool tp;
+    const CameraParams &C = P.cam;
+    const TileMap tm = map_tile(C);
+    pool_init(tp);
+    const uint32_t total_items = C.max_depth > 0 ? tm.n_valid * P.sample_count : 0u;
+    PoolLane L;
+    TraversalCounters ctr;
+    Hit best{0.0, kNoHit};
+    while (pool_shade_and_advance(P, tm, tp, total_items, best, L)) {
+        // world.hit_by(ray, Interval::with_min(0.00001))  (camera.h:217)
+        best = closest_hit<STACK, COUNT, SHALLOW>(P.scene, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001,
+                                                  __longlong_as_double(0x7ff0000000000000LL), &ctr);
+    }
+    pool_write_tile(P, tm, tp);
+    write_counters(P, L.rays, COUNT, ctr);
+}
+
+// ------------------------------------------------------------------------------------------
+// path_megakernel (thread-owns-pixel form, kept for A/B: B200RT_FLAG_THREAD_PIXELS): every lane runs traverse-then-shade
+// in a loop over ITS pixel's samples and starts the next sample as soon as a path ends.  64 registers (16 blocks = 32 warps per SM) measured
 // fastest on B200: 8/12/16/20/24 blocks per SM gave 2707/3171/3263/2630/2307 Mpaths/s on C2.
 template <int STACK, bool COUNT, bool SHALLOW = false, int MINB = kPathMinBlocks>
 __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel(const __grid_constant__ RenderParams P) {
@@ -221,16 +364,21 @@ __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel(const __grid
 //   acc[12] primitive-test executions (a leaf step loops over its primitives)            acc[13] lanes taking part
 //   acc[14] warps   acc[15] lane-rounds (shade calls that started a ray)
 // Same Philox keys and the same arithmetic as path_megakernel, so it also writes the same image.
-template <int STACK>
+template <int STACK, bool POOL>
 __global__ void __launch_bounds__(kPathBlock) path_lanes_kernel(const __grid_constant__ RenderParams P, unsigned long long *__restrict__ acc) {
+    __shared__ TilePool tp;
     const CameraParams &C = P.cam;
     const PixelMap m = map_pixel(C);
+    const TileMap tm = map_tile(C);
+    if (POOL) pool_init(tp);
+    const uint32_t total_items = C.max_depth > 0 ? tm.n_valid * P.sample_count : 0u;
     LaneState L;
+    PoolLane Lp;
     Trav T;
     uint2 stack[STACK];
     T.cur = kTravDone;
     T.best.t = 0.0; T.best.ref = kNoHit;
-    bool finished = !(m.valid && C.max_depth > 0 && P.sample_count > 0);
+    bool finished = POOL ? false : !(m.valid && C.max_depth > 0 && P.sample_count > 0);
     unsigned long long a[16] = {};
     const unsigned full = 0xffffffffu;
     while (true) {
@@ -238,13 +386,16 @@ __global__ void __launch_bounds__(kPathBlock) path_lanes_kernel(const __grid_con
         if (!ms) break;
         a[0]++; a[1] += __popc(ms);
         if (!finished) {
-            if (shade_and_advance(P, m, T.best, L)) {
-                a[15]++;
-                trav_init(T, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001, __longlong_as_double(0x7ff0000000000000LL));
+            bool go;
+            if (POOL) {
+                go = pool_shade_and_advance(P, tm, tp, total_items, T.best, Lp);
+                if (go) trav_init(T, Lp.ray.ox, Lp.ray.oy, Lp.ray.oz, Lp.ray.dx, Lp.ray.dy, Lp.ray.dz, 0.00001, __longlong_as_double(0x7ff0000000000000LL));
             } else {
-                finished = true;
-                T.cur = kTravDone;
+                go = shade_and_advance(P, m, T.best, L);
+                if (go) trav_init(T, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001, __longlong_as_double(0x7ff0000000000000LL));
             }
+            if (go) a[15]++;
+            else { finished = true; T.cur = kTravDone; }
         }
         while (true) {
             const bool node = !finished && trav_at_node(T), leaf = !finished && trav_at_leaf(T);
@@ -266,7 +417,8 @@ __global__ void __launch_bounds__(kPathBlock) path_lanes_kernel(const __grid_con
         }
     }
     TraversalCounters ctr;
-    write_pixel_and_counters(P, m, L.sum_r, L.sum_g, L.sum_b, L.rays, false, ctr);
+    if (POOL) { pool_write_tile(P, tm, tp); write_counters(P, Lp.rays, false, ctr); }
+    else write_pixel_and_counters(P, m, L.sum_r, L.sum_g, L.sum_b, L.rays, false, ctr);
     a[14] = 1;
     unsigned long long rounds = a[15];
     for (int off = 16; off; off >>= 1) rounds += __shfl_down_sync(full, rounds, off);
@@ -434,6 +586,14 @@ template <int STACK>
 static cudaError_t launch_path_t(const RenderParams &P, bool count, bool shallow, cudaStream_t st) {
     const uint32_t tiles = ((P.cam.w + 7u) >> 3) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
     if (tiles == 0) return cudaSuccess;
+    if (!(P.flags & kRenderThreadPixels)) {
+        if (STACK == 32 && shallow) {   // trees of depth <= 3 (a handful of nodes): while-while loop structure
+            if (count) path_megakernel_pool<32, true, true><<<tiles, kPathBlock, 0, st>>>(P);
+            else path_megakernel_pool<32, false, true><<<tiles, kPathBlock, 0, st>>>(P);
+        } else if (count) path_megakernel_pool<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
+        else path_megakernel_pool<STACK, false><<<tiles, kPathBlock, 0, st>>>(P);
+        return cudaGetLastError();
+    }
     if (STACK == 32 && shallow) {   // trees of depth <= 3 (a handful of nodes): while-while loop structure
         if (count) path_megakernel<32, true, true><<<tiles, kPathBlock, 0, st>>>(P);
         else path_megakernel<32, false, true><<<tiles, kPathBlock, 0, st>>>(P);
@@ -451,9 +611,10 @@ cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count,
 cudaError_t launch_path_lanes(int stack, const RenderParams &P, unsigned long long *acc, cudaStream_t st) {
     const uint32_t tiles = ((P.cam.w + 7u) >> 3) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
     if (tiles == 0) return cudaSuccess;
-    if (stack <= 32) path_lanes_kernel<32><<<tiles, kPathBlock, 0, st>>>(P, acc);
-    else if (stack <= 64) path_lanes_kernel<64><<<tiles, kPathBlock, 0, st>>>(P, acc);
-    else path_lanes_kernel<128><<<tiles, kPathBlock, 0, st>>>(P, acc);
+    const bool pool = !(P.flags & kRenderThreadPixels);
+    if (stack <= 32) { if (pool) path_lanes_kernel<32, true><<<tiles, kPathBlock, 0, st>>>(P, acc); else path_lanes_kernel<32, false><<<tiles, kPathBlock, 0, st>>>(P, acc); }
+    else if (stack <= 64) { if (pool) path_lanes_kernel<64, true><<<tiles, kPathBlock, 0, st>>>(P, acc); else path_lanes_kernel<64, false><<<tiles, kPathBlock, 0, st>>>(P, acc); }
+    else { if (pool) path_lanes_kernel<128, true><<<tiles, kPathBlock, 0, st>>>(P, acc); else path_lanes_kernel<128, false><<<tiles, kPathBlock, 0, st>>>(P, acc); }
     return cudaGetLastError();
 }
 

@@ -17,7 +17,9 @@ constexpr int kPathMinBlocks = B200RT_PATH_MINB;    // occupancy experiments
 #else
 constexpr int kPathMinBlocks = 1024 / kPathBlock;   // 1024 threads = 32 warps per SM at 64 registers
 #endif
-constexpr uint32_t kRenderAccumulate = 2u;   // == B200RT_FLAG_ACCUMULATE
+constexpr uint32_t kRenderAccumulate = 2u;    // == B200RT_FLAG_ACCUMULATE
+constexpr uint32_t kRenderThreadPixels = 16u; // == B200RT_FLAG_THREAD_PIXELS
+constexpr uint32_t kMaxSamplesPerLaunch = 1u << 24;   // tile items (64 pixels x samples) are counted in 32 bits
 
 struct RenderParams {
     DeviceScene scene;

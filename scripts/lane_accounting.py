@@ -9,6 +9,7 @@ from cpp_raytracer_b200 import scene_io, build
 CFG = {"C1": ("rtow_final", 1200, 675, 20), "C2": ("rtow_lights", 1920, 1080, 20), "C3": ("cornell", 1024, 1024, 1000),
        "C4": ("xmas", 1920, 1080, 50), "C4b": ("raining", 1920, 1080, 50), "C5": ("millions_lights", 3840, 2160, 20)}
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+FLAGS = int(os.environ.get("FLAGS", "0"))     # 16 = B200RT_FLAG_THREAD_PIXELS (round-1 work distribution)
 # instruction weights per executed step (SASS counts, profiles/r1_final_megakernel_C2_1024spp_ncu.md)
 W_NODE, W_PRIM_SPHERE, W_PRIM_QUAD, W_SHADE = 160.0, 135.0, 150.0, 350.0
 for tag in os.environ.get("ONLY", "C1,C2,C3,C4,C4b,C5").split(","):
@@ -18,11 +19,11 @@ for tag in os.environ.get("ONLY", "C1,C2,C3,C4,C4b,C5").split(","):
     s = scene_io.load_scene(p)
     cam = rt.camera_with(s.camera, image_w=w, image_h=h, spp=spp, max_depth=depth)
     with rt.DeviceSceneHandle(s) as d:
-        a = [int(x) for x in d.lane_accounting(cam)]
+        a = [int(x) for x in d.lane_accounting(cam, flags=FLAGS)]
     wp = W_PRIM_QUAD if len(s.quads) > len(s.spheres) else W_PRIM_SPHERE
     slots = 32.0 * (a[0] * W_SHADE + a[2] * W_NODE + a[12] * wp)          # lane-slots issued, instruction weighted
     used = a[1] * W_SHADE + a[3] * W_NODE + a[13] * wp
-    out = {"cfg": tag, "spp": spp, "raw": a,
+    out = {"cfg": tag, "spp": spp, "work_distribution": "thread owns pixel" if FLAGS & 16 else "tile work pool", "raw": a,
            "lanes_per_shade": a[1] / max(1, a[0]), "lanes_per_node_step": a[3] / max(1, a[2]),
            "lanes_per_leaf_step": a[8] / max(1, a[7]), "lanes_per_prim_test": a[13] / max(1, a[12]),
            "node_execs_per_ray": 32.0 * a[2] / max(1, a[15]), "prim_execs_per_ray": 32.0 * a[12] / max(1, a[15]),

@@ -9,6 +9,7 @@ from cpp_raytracer_b200 import scene_io, capi, build
 spp = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 variant = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 leaf = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+FLAGS = int(os.environ.get("FLAGS", "0"))     # e.g. FLAGS=16: B200RT_FLAG_THREAD_PIXELS (A/B against the tile work pool)
 CFG = [("C1", "rtow_final", 1200, 675, 20), ("C2", "rtow_lights", 1920, 1080, 20), ("C3", "cornell", 1024, 1024, 1000),
        ("C4", "xmas", 1920, 1080, 50), ("C4b", "raining", 1920, 1080, 50), ("C5", "millions_lights", 3840, 2160, 20)]
 only = os.environ.get("ONLY")
@@ -24,9 +25,9 @@ for tag, name, w, h, depth in CFG:
     t0 = time.time()
     with rt.DeviceSceneHandle(s, max_leaf_prims=leaf) as d:
         info = d.info()
-        d.render(rt.camera_with(cam, spp=max(1, spp // 8)), variant=variant)
-        _, st = d.render(cam, variant=variant)
-        _, sc = d.render(rt.camera_with(cam, spp=max(1, spp // 8)), flags=capi.FLAG_COUNTERS, variant=variant)
+        d.render(rt.camera_with(cam, spp=max(1, spp // 8)), variant=variant, flags=FLAGS)
+        _, st = d.render(cam, variant=variant, flags=FLAGS)
+        _, sc = d.render(rt.camera_with(cam, spp=max(1, spp // 8)), flags=capi.FLAG_COUNTERS | FLAGS, variant=variant)
     print(json.dumps({"cfg": tag, "scene": name, "res": f"{w}x{h}", "spp": spp, "prims": info["n_prims"], "nodes": info["n_nodes"],
                       "depth": info["tree_depth"], "build_ms": round(info["build_ms"]), "MB": round(info["device_bytes"] / 1e6, 1),
                       "kernel_ms": round(st["kernel_ms"], 2), "Mpaths/s": round(st["paths"] / st["kernel_ms"] / 1e3, 1),
