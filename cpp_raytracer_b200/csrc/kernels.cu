@@ -222,7 +222,6 @@ __device__ __forceinline__ TileMap map_tile(const CameraParams &C) {
 
 struct PoolLane {
     PathState p;
-    Ray ray;
     uint32_t pixel = 0, lp = 0, s = 0, bounce = 0;    // image pixel index, pixel within the tile, sample, bounce
     bool has_path = false;
     uint32_t rays = 0;
@@ -236,7 +235,7 @@ __device__ __forceinline__ void pool_contribute(TilePool &tp, uint32_t lp, float
 
 // shade_and_advance with the tile pool: same path semantics, same Philox keys (pixel, sample, bounce).
 __device__ __forceinline__ bool pool_shade_and_advance(const RenderParams &P, const TileMap &tm, TilePool &tp, uint32_t total_items,
-                                                       const Hit &best, PoolLane &L) {
+                                                       const Hit &best, PoolLane &L, Ray &ray) {
     const CameraParams &C = P.cam;
     const uint32_t k0 = (uint32_t)P.seed, k1 = (uint32_t)(P.seed >> 32);
     if (L.has_path) {
@@ -248,7 +247,7 @@ __device__ __forceinline__ bool pool_shade_and_advance(const RenderParams &P, co
             cont = false;   // camera.h:248
         } else {
             const Philox4 rnd = philox4x32_10(L.pixel, P.sample_begin + L.s, L.bounce + 1u, 0u, k0, k1);
-            cont = shade_hit(P.scene, best, rnd, L.ray, L.p, er, eg, eb);
+            cont = shade_hit(P.scene, best, rnd, ray, L.p, er, eg, eb);
             // ray_color(scattered, depth_left - 1): contributes nothing once depth_left hits 0 (camera.h:211-213)
             if (cont && ++L.bounce == C.max_depth) cont = false;
         }
@@ -264,7 +263,7 @@ __device__ __forceinline__ bool pool_shade_and_advance(const RenderParams &P, co
         const uint32_t px = tm.x0 + lx, py = tm.y0 + ly;
         L.pixel = py * C.w + px;
         const Philox4 rnd = philox4x32_10(L.pixel, P.sample_begin + L.s, 0u, 0u, k0, k1);
-        camera_ray(C, px, py, rnd, L.ray, L.p);
+        camera_ray(C, px, py, rnd, ray, L.p);
         L.bounce = 0;
         L.has_path = true;
     }
@@ -320,11 +319,12 @@ __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel_pool(const _
     pool_init(tp);
     const uint32_t total_items = C.max_depth > 0 ? tm.n_valid * P.sample_count : 0u;
     PoolLane L;
+    Ray ray;
     TraversalCounters ctr;
     Hit best{0.0, kNoHit};
-    while (pool_shade_and_advance(P, tm, tp, total_items, best, L)) {
+    while (pool_shade_and_advance(P, tm, tp, total_items, best, L, ray)) {
         // world.hit_by(ray, Interval::with_min(0.00001))  (camera.h:217)
-        best = closest_hit<STACK, COUNT, SHALLOW>(P.scene, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001,
+        best = closest_hit<STACK, COUNT, SHALLOW>(P.scene, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, 0.00001,
                                                   __longlong_as_double(0x7ff0000000000000LL), &ctr);
     }
     pool_write_tile(P, tm, tp);
@@ -388,8 +388,8 @@ __global__ void __launch_bounds__(kPathBlock) path_lanes_kernel(const __grid_con
         if (!finished) {
             bool go;
             if (POOL) {
-                go = pool_shade_and_advance(P, tm, tp, total_items, T.best, Lp);
-                if (go) trav_init(T, Lp.ray.ox, Lp.ray.oy, Lp.ray.oz, Lp.ray.dx, Lp.ray.dy, Lp.ray.dz, 0.00001, __longlong_as_double(0x7ff0000000000000LL));
+                go = pool_shade_and_advance(P, tm, tp, total_items, T.best, Lp, T.ray);
+                if (go) trav_setup(T, 0.00001, __longlong_as_double(0x7ff0000000000000LL));
             } else {
                 go = shade_and_advance(P, m, T.best, L);
                 if (go) trav_init(T, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001, __longlong_as_double(0x7ff0000000000000LL));

@@ -29,7 +29,7 @@ struct RenderParams {
     float *out;                        // image_h x image_w x 3
     float scale;                       // 1 (sum) or 1/sample_count (mean)
     uint32_t flags;
-    unsigned long long *counters;      // [0] rays, [1] node visits, [2] primitive tests
+    unsigned long long *counters;      // [0] rays, [1] node visits, [2] primitive tests, [3] of which quad tests
 };
 
 // Path-slot pool of the wavefront variant (wavefront.cu); all pointers are device memory.

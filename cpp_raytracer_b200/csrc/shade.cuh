@@ -21,10 +21,6 @@ struct CameraParams {
     uint32_t w, h, max_depth;
 };
 
-struct Ray {
-    double ox, oy, oz, dx, dy, dz;   // direction NOT normalised, as in the reference (ray3d.h)
-};
-
 struct PathState {
     float tr, tg, tb;   // throughput (product of attenuations so far)
 };

@@ -57,6 +57,10 @@ constexpr uint32_t kQuadFlagD = 0x40000000u;
 constexpr uint32_t kNoHit = 0xFFFFFFFFu;
 constexpr float kBoxSlack = 1.0f + 1e-6f;      // covers inv rounding (2^-23) + FMA rounding (2^-24) on both sides: 3.6e-7
 
+struct Ray {
+    double ox, oy, oz, dx, dy, dz;   // direction NOT normalised, as in the reference (ray3d.h)
+};
+
 struct Hit {
     double t;
     uint32_t ref;   // kNoHit, or (kQuadFlagD?) | index into the leaf-ordered per-type array
@@ -161,7 +165,7 @@ constexpr uint32_t kTravDone = 0xFFFFFFFFu;   // `cur` value once the stack has 
 // so that kernels can either run them in a plain loop (closest_hit below) or let a warp vote
 // on which kind of step to execute next (path_megakernel).
 struct Trav {
-    double ox, oy, oz, dx, dy, dz;   // the ray, exactly as given (FP64; direction not normalised)
+    Ray ray;                         // the ray, exactly as given (FP64; direction not normalised)
     double a;                        // dot(dir, dir), hoisted out of Sphere::hit_by (sphere.h:49)
     double tmin;
     Hit best;                        // best.t doubles as the shrinking ray_times.max (bvh.h:651)
@@ -204,9 +208,9 @@ __device__ __forceinline__ void trav_axis(double o, double d, float &inv, float 
     cf = r == 0.0f ? __int_as_float(0xff800000) : __double2float_rd(p - pad);
 }
 
-__device__ __forceinline__ void trav_init(Trav &T, double ox, double oy, double oz, double dx, double dy, double dz,
-                                          double tmin, double tmax) {
-    T.ox = ox; T.oy = oy; T.oz = oz; T.dx = dx; T.dy = dy; T.dz = dz;
+// Starts the traversal of the ray already stored in T.ray.
+__device__ __forceinline__ void trav_setup(Trav &T, double tmin, double tmax) {
+    const double ox = T.ray.ox, oy = T.ray.oy, oz = T.ray.oz, dx = T.ray.dx, dy = T.ray.dy, dz = T.ray.dz;
     // Slab tests are  t = plane * inv - o * inv  as ONE FMA per plane.  The product o * inv is formed in
     // double from the exact origin and rounded outward (plus a relative pad that also makes the
     // bound strict), so the origin is never rounded to FP32 and the only relative errors left are
@@ -226,6 +230,11 @@ __device__ __forceinline__ void trav_init(Trav &T, double ox, double oy, double 
     T.best.ref = kNoHit;
     T.sp = 0;
     T.cur = 0;   // root
+}
+__device__ __forceinline__ void trav_init(Trav &T, double ox, double oy, double oz, double dx, double dy, double dz,
+                                          double tmin, double tmax) {
+    T.ray.ox = ox; T.ray.oy = oy; T.ray.oz = oz; T.ray.dx = dx; T.ray.dy = dy; T.ray.dz = dz;
+    trav_setup(T, tmin, tmax);
 }
 
 // Pops the next stack entry that can still contain a closer hit into T.cur (kTravDone if none).
@@ -297,13 +306,13 @@ __device__ __forceinline__ uint32_t trav_leaf_step(const DeviceScene &S, Trav &T
         uint32_t ref;
         if (is_quad) {
             ref = kQuadFlagD | (first + i);
-            hit = quad_root(T.ox, T.oy, T.oz, T.dx, T.dy, T.dz, S.quads + (size_t)(first + i) * 8, T.tmin, T.best.t,
+            hit = quad_root(T.ray.ox, T.ray.oy, T.ray.oz, T.ray.dx, T.ray.dy, T.ray.dz, S.quads + (size_t)(first + i) * 8, T.tmin, T.best.t,
                             T.best.ref != kNoHit, t);
         } else {
             ref = first + i;
             const double2 s0 = __ldg(S.spheres + (size_t)(first + i) * 2);
             const double2 s1 = __ldg(S.spheres + (size_t)(first + i) * 2 + 1);
-            hit = sphere_root(T.ox, T.oy, T.oz, T.dx, T.dy, T.dz, T.a, s0.x, s0.y, s1.x, s1.y, T.tmin, T.best.t,
+            hit = sphere_root(T.ray.ox, T.ray.oy, T.ray.oz, T.ray.dx, T.ray.dy, T.ray.dz, T.a, s0.x, s0.y, s1.x, s1.y, T.tmin, T.best.t,
                               T.best.ref != kNoHit, t);
         }
         // strictly closer wins; an exact tie goes to the lower canonical index (scene.h:59-75)
