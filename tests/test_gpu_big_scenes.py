@@ -102,10 +102,12 @@ def test_host_cpp_render_call_writes_reference_format_ppm(scenes_bin, golden, tm
     assert np.array_equal(got, rt.tonemap(img))
 
 
-@pytest.mark.parametrize("name,w,h,spp", [("rtow_lights", 1920, 1080, 16), ("xmas", 1920, 1080, 8)])
+@pytest.mark.parametrize("name,w,h,spp", [("rtow_lights", 1920, 1080, 16), ("xmas", 1920, 1080, 8),
+                                          ("cornell", 1024, 1024, 16), ("millions_lights", 3840, 2160, 4)])
 def test_full_resolution_frame_converges_to_live_reference(scenes_bin, ref_bridge, name, w, h, spp, tmp_path):
-    """BASELINE-size frames (C2 / C4 resolution) against two live reference renders of the same
-    size: the GPU-vs-reference RMSE sits on the reference-vs-reference noise floor."""
+    """BASELINE-size frames (C2 / C4 resolution, C3's 1024^2 at depth 1000, C5's 3840x2160 over 3.1 M spheres) against
+    two live reference renders of the same size: the GPU-vs-reference RMSE sits on the reference-vs-reference noise
+    floor."""
     if ref_bridge is None:
         pytest.skip("oracle/_ref/ref_bridge not built")
     import cpp_raytracer_b200 as rt
