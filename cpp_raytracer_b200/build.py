@@ -96,6 +96,26 @@ def build_debug(force: bool = False) -> str:
     return LIB_DBG
 
 
+def build_variant(name: str, extra_flags: list) -> str:
+    """An experiment build of the same sources with extra -D flags -> scratch_libs/libb200rt_<name>.so (git-ignored,
+    travels to the GPU box; select it with B200RT_LIB).  For A/B measurements in one gpurun call."""
+    out_dir = os.path.join(os.path.dirname(HERE), "scratch_libs")
+    os.makedirs(out_dir, exist_ok=True)
+    out = os.path.join(out_dir, f"libb200rt_{name}.so")
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, *extra_flags, "-o", out, *[os.path.join(CSRC, s) for s in SOURCES], "-lpthread"]
+    env = dict(os.environ)
+    env.pop("CXX", None)
+    env.pop("CC", None)
+    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+    with open(out + ".log", "w") as f:
+        f.write(" ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError(f"nvcc failed building {out}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB

@@ -107,18 +107,18 @@ __global__ void __launch_bounds__(128) debug_shade_kernel(DeviceScene S, const d
 }
 
 // ------------------------------------------------------------------------------------------
-// Thread -> pixel: a block is an 8x8 pixel tile, each warp an 8x4 sub-tile, so the 32 primary
+// Thread -> pixel: a block is an 8 x (kPathBlock / 8) pixel tile, each warp an 8x4 sub-tile, so the 32 primary
 // rays of a warp are neighbours on the image plane.
 struct PixelMap {
     uint32_t px, py, pixel;
     bool valid;
 };
 __device__ __forceinline__ PixelMap map_pixel(const CameraParams &C) {
-    const uint32_t tiles_x = (C.w + 7u) >> 3;
+    const uint32_t tiles_x = (C.w + (uint32_t)kPathTileW - 1u) / (uint32_t)kPathTileW;
     const uint32_t tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
     PixelMap m;
-    m.px = tile_x * 8u + (threadIdx.x & 7u);
-    m.py = tile_y * (uint32_t)kPathTileH + (threadIdx.x >> 3);
+    m.px = tile_x * (uint32_t)kPathTileW + (threadIdx.x % (uint32_t)kPathTileW);
+    m.py = tile_y * (uint32_t)kPathTileH + (threadIdx.x / (uint32_t)kPathTileW);
     m.valid = m.px < C.w && m.py < C.h;
     m.pixel = m.py * C.w + m.px;
     return m;
@@ -189,7 +189,7 @@ __device__ __forceinline__ bool shade_and_advance(const RenderParams &P, const P
 }
 
 // ------------------------------------------------------------------------------------------
-// Tile work pool.  A block owns an 8 x 8 pixel tile but its THREADS do not own pixels: the tile's (pixel, sample) items
+// Tile work pool.  A block owns an 8 x 32 pixel tile (kPathTileW x kPathTileH) but its THREADS do not own pixels: the tile's (pixel, sample) items
 // -- sample-major, so that the lanes of a warp work on neighbouring pixels of the same sample at any time -- are handed
 // out through a shared-memory counter, and a lane whose path ends takes the next item whatever pixel it belongs to.
 // With thread-owns-pixel a lane on a cheap pixel (sky: one ray per path) ran out of samples long before its neighbours
@@ -210,12 +210,12 @@ struct TileMap {
     uint32_t x0, y0, vw, n_valid;      // tile origin, valid width, valid pixel count (edge tiles are ragged)
 };
 __device__ __forceinline__ TileMap map_tile(const CameraParams &C) {
-    const uint32_t tiles_x = (C.w + 7u) >> 3;
+    const uint32_t tiles_x = (C.w + (uint32_t)kPathTileW - 1u) / (uint32_t)kPathTileW;
     const uint32_t tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
     TileMap t;
-    t.x0 = tile_x * 8u;
+    t.x0 = tile_x * (uint32_t)kPathTileW;
     t.y0 = tile_y * (uint32_t)kPathTileH;
-    t.vw = min(8u, C.w - t.x0);
+    t.vw = min((uint32_t)kPathTileW, C.w - t.x0);
     t.n_valid = t.vw * min((uint32_t)kPathTileH, C.h - t.y0);
     return t;
 }
@@ -259,7 +259,8 @@ __device__ __forceinline__ bool pool_shade_and_advance(const RenderParams &P, co
         if (item >= total_items) return false;
         if (tm.n_valid == (uint32_t)kPathBlock) { L.s = item / (uint32_t)kPathBlock; L.lp = item % (uint32_t)kPathBlock; }
         else { L.s = item / tm.n_valid; L.lp = item - L.s * tm.n_valid; }
-        const uint32_t lx = tm.vw == 8u ? (L.lp & 7u) : L.lp % tm.vw, ly = tm.vw == 8u ? (L.lp >> 3) : L.lp / tm.vw;
+        const uint32_t lx = tm.vw == (uint32_t)kPathTileW ? L.lp % (uint32_t)kPathTileW : L.lp % tm.vw;
+        const uint32_t ly = tm.vw == (uint32_t)kPathTileW ? L.lp / (uint32_t)kPathTileW : L.lp / tm.vw;
         const uint32_t px = tm.x0 + lx, py = tm.y0 + ly;
         L.pixel = py * C.w + px;
         const Philox4 rnd = philox4x32_10(L.pixel, P.sample_begin + L.s, 0u, 0u, k0, k1);
@@ -584,7 +585,7 @@ cudaError_t launch_debug_shade(int stack, const DeviceScene &S, const double *ra
 
 template <int STACK>
 static cudaError_t launch_path_t(const RenderParams &P, bool count, bool shallow, cudaStream_t st) {
-    const uint32_t tiles = ((P.cam.w + 7u) >> 3) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
+    const uint32_t tiles = ((P.cam.w + (uint32_t)kPathTileW - 1u) / (uint32_t)kPathTileW) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
     if (tiles == 0) return cudaSuccess;
     if (!(P.flags & kRenderThreadPixels)) {
         if (STACK == 32 && shallow) {   // trees of depth <= 3 (a handful of nodes): while-while loop structure
@@ -609,7 +610,7 @@ cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count,
 }
 
 cudaError_t launch_path_lanes(int stack, const RenderParams &P, unsigned long long *acc, cudaStream_t st) {
-    const uint32_t tiles = ((P.cam.w + 7u) >> 3) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
+    const uint32_t tiles = ((P.cam.w + (uint32_t)kPathTileW - 1u) / (uint32_t)kPathTileW) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
     if (tiles == 0) return cudaSuccess;
     const bool pool = !(P.flags & kRenderThreadPixels);
     if (stack <= 32) { if (pool) path_lanes_kernel<32, true><<<tiles, kPathBlock, 0, st>>>(P, acc); else path_lanes_kernel<32, false><<<tiles, kPathBlock, 0, st>>>(P, acc); }

@@ -7,11 +7,20 @@
 
 namespace b200rt {
 
+// Threads per block of the path kernels = pixels per tile of the work pool.  Measured with the pool (B200, 128 spp,
+// gpurun_out/r2_variants*.txt -> profiles/r2_tile_shape.md): 8 x 8 / 8 x 16 / 8 x 32 / 8 x 64 / 8 x 128 tiles give
+// C2 4020 / 4104 / 4135 / 4134 / 4171 and C4b 3243 / 3384 / 3580 / 3576 / 3629 Mpaths/s; 16- and 32-wide tiles are
+// slower than 8-wide ones of the same size (the 32 consecutive items a warp holds form an 8 x 4 pixel patch).
 #ifndef B200RT_PATH_BLOCK
-#define B200RT_PATH_BLOCK 64
+#define B200RT_PATH_BLOCK 256
 #endif
-constexpr int kPathBlock = B200RT_PATH_BLOCK;       // threads per block of the path kernels: an 8 x (kPathBlock/8) pixel tile
-constexpr int kPathTileH = kPathBlock / 8;
+#ifndef B200RT_TILE_W
+#define B200RT_TILE_W 8
+#endif
+constexpr int kPathBlock = B200RT_PATH_BLOCK;       // threads per block of the path kernels = pixels per tile
+constexpr int kPathTileW = B200RT_TILE_W;           // tile = kPathTileW x (kPathBlock / kPathTileW) pixels
+constexpr int kPathTileH = kPathBlock / kPathTileW;
+static_assert(kPathBlock % kPathTileW == 0 && kPathBlock % 32 == 0, "tile shape");
 #ifdef B200RT_PATH_MINB
 constexpr int kPathMinBlocks = B200RT_PATH_MINB;    // occupancy experiments
 #else

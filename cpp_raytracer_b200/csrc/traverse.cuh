@@ -82,6 +82,28 @@ __device__ __forceinline__ uint32_t canonical_prim(const DeviceScene &S, uint32_
 __device__ __forceinline__ bool sphere_root(double ox, double oy, double oz, double dx, double dy, double dz,
                                             double a, double cx, double cy, double cz, double r,
                                             double tmin, double tmax, bool tie_ok, double &root_out) {
+#ifdef B200RT_EXP_FP32_LEAF
+    // EXPERIMENT ONLY (breaks parity): the sphere test in plain FP32, origin difference formed in double.  Measures
+    // the CEILING of any scheme that takes FP64 out of the traversal (deferred exact tests, FP32 intervals): such a
+    // scheme still does at least this much work per leaf step.
+    {
+        const float ocx = (float)(ox - cx), ocy = (float)(oy - cy), ocz = (float)(oz - cz);
+        const float fdx = (float)dx, fdy = (float)dy, fdz = (float)dz, fa = (float)a, fr = (float)r;
+        const float b_half = fdx * ocx + fdy * ocy + fdz * ocz;
+        const float c = (ocx * ocx + ocy * ocy + ocz * ocz) - fr * fr;
+        const float disc = b_half * b_half - fa * c;
+        if (disc < 0) return false;
+        const float sq = sqrtf(disc);
+        const float inv_a = __frcp_rn(fa);
+        float root = (-b_half - sq) * inv_a;
+        if (!((float)tmin < root && root < (float)tmax)) {
+            root = (-b_half + sq) * inv_a;
+            if (!((float)tmin < root && root < (float)tmax)) return false;
+        }
+        root_out = (double)root;
+        return true;
+    }
+#endif
     const double ocx = ox - cx, ocy = oy - cy, ocz = oz - cz;
     const double b_half = dx * ocx + dy * ocy + dz * ocz;
     const double c = (ocx * ocx + ocy * ocy + ocz * ocz) - r * r;

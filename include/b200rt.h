@@ -121,7 +121,7 @@ enum {
     B200RT_FLAG_COUNTERS = 4,     /* also count node visits and primitive tests (slower; for roofline accounting) */
     B200RT_FLAG_THREAD_PIXELS = 16, /* A/B switch: the round-1 work distribution (a thread owns a pixel and renders all its
                                      samples) instead of the tile work pool (threads take (pixel, sample) items of their
-                                     8x8 tile as their paths end).  Same paths, same image up to summation order. */
+                                     8 x 32 tile as their paths end).  Same paths, same image up to summation order. */
     B200RT_FLAG_EXACT_COUNT = 8   /* sample_count is taken literally: 0 renders NO samples (the output is zeroed /
                                      left alone under ACCUMULATE) instead of meaning "camera.spp" -- what a rank of a
                                      sample split whose share is empty (spp < ranks) must pass */
