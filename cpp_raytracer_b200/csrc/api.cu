@@ -323,6 +323,9 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
     P.flags = o.flags;
     P.scale = (o.flags & B200RT_FLAG_SUM) || count == 0 ? 1.0f : (float)(1.0 / (double)count);
     P.counters = s->d_counters;
+    // work-pool item order (kernels.cu): same-pixel groups of 8 when only light hits contribute (black background)
+    P.group_shift = (cam->background[0] == 0.0 && cam->background[1] == 0.0 && cam->background[2] == 0.0) ? 3u : 0u;
+    if (const char *g = std::getenv("B200RT_GROUP_SHIFT")) P.group_shift = (uint32_t)std::min(5, std::max(0, std::atoi(g)));   // experiments
     CUDA_TRY(cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), st));
     unsigned long long launches = 1;
     CUDA_TRY(cudaEventRecord(s->ev0, st));
@@ -1046,6 +1049,7 @@ int b200rt_debug_lane_accounting(void *scene, const B200rtCamera *cam, const B20
     if (e == cudaSuccess) e = cudaMemsetAsync(s->d_counters, 0, 4 * sizeof(unsigned long long), 0);
     P.scene = s->d; P.seed = o.seed; P.sample_begin = (uint32_t)o.sample_offset; P.sample_count = (uint32_t)count;
     P.out = d_frame; P.flags = o.flags & B200RT_FLAG_THREAD_PIXELS; P.scale = 1.0f; P.counters = s->d_counters;
+    P.group_shift = (cam->background[0] == 0.0 && cam->background[1] == 0.0 && cam->background[2] == 0.0) ? 3u : 0u;
     if (e == cudaSuccess) e = launch_path_lanes(s->stack, P, d_acc, 0);
     if (e == cudaSuccess) e = cudaMemcpy(counters_out, d_acc, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaStreamSynchronize(0);

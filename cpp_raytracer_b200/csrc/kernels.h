@@ -28,7 +28,7 @@ constexpr int kPathMinBlocks = 1024 / kPathBlock;   // 1024 threads = 32 warps p
 #endif
 constexpr uint32_t kRenderAccumulate = 2u;    // == B200RT_FLAG_ACCUMULATE
 constexpr uint32_t kRenderThreadPixels = 16u; // == B200RT_FLAG_THREAD_PIXELS
-constexpr uint32_t kMaxSamplesPerLaunch = 1u << 24;   // tile items (64 pixels x samples) are counted in 32 bits
+constexpr uint32_t kMaxSamplesPerLaunch = 1u << 22;   // tile items (up to 1024 pixels x samples, + one group) are counted in 32 bits
 
 struct RenderParams {
     DeviceScene scene;
@@ -39,6 +39,7 @@ struct RenderParams {
     float scale;                       // 1 (sum) or 1/sample_count (mean)
     uint32_t flags;
     unsigned long long *counters;      // [0] rays, [1] node visits, [2] primitive tests, [3] of which quad tests
+    uint32_t group_shift;              // work-pool item order: 2^group_shift consecutive items are samples of one pixel
 };
 
 // Path-slot pool of the wavefront variant (wavefront.cu); all pointers are device memory.

@@ -22,6 +22,9 @@ for tag, name, w, h, depth in CFG:
     subprocess.run([binp, name, "dump", p], check=True, capture_output=True)
     s = scene_io.load_scene(p)
     cam = rt.camera_with(s.camera, image_w=w, image_h=h, spp=spp, max_depth=depth)
+    if os.environ.get("BG"):                         # experiment: override the background (e.g. BG=0 or BG=0.7,0.8,1)
+        bg = [float(x) for x in os.environ["BG"].split(",")]
+        cam = rt.camera_with(cam, background=bg * 3 if len(bg) == 1 else bg)
     t0 = time.time()
     with rt.DeviceSceneHandle(s, max_leaf_prims=leaf) as d:
         info = d.info()

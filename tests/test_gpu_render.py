@@ -60,6 +60,35 @@ def test_render_converges_to_reference(golden, name):
     assert lerr <= 0.02 + 3 * abs(lum(tA) - lum(tB)) / lref
 
 
+@pytest.mark.parametrize("name", ["rtow_final", "rtow_lights", "cornell"])
+def test_image_does_not_depend_on_the_work_distribution(golden, name):
+    """The tile work pool hands (pixel, sample) items to whichever lane is free, in sample-major order or in same-pixel
+    groups (chosen by the background; B200RT_GROUP_SHIFT overrides); radiance is summed per pixel in 64-bit fixed point,
+    which is order independent -- so the image must be the SAME BITS under every item order, for ragged sample counts
+    and ragged tiles, and equal up to FP32 summation order to the round-1 distribution (a thread owns a pixel)."""
+    import os
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    scene = golden.scene(name)
+    for (w, h, spp) in ((203, 117, 21), (61, 300, 5), (8, 32, 64)):
+        cam = rt.camera_with(scene.camera, image_w=w, image_h=h, spp=spp, max_depth=25)
+        imgs = {}
+        with rt.DeviceSceneHandle(scene) as dev:
+            for g in ("0", "1", "3", "5"):
+                os.environ["B200RT_GROUP_SHIFT"] = g
+                try:
+                    imgs[g], st = dev.render(cam, seed=5)
+                finally:
+                    del os.environ["B200RT_GROUP_SHIFT"]
+            auto, st_auto = dev.render(cam, seed=5)
+            old, st_old = dev.render(cam, seed=5, flags=capi.FLAG_THREAD_PIXELS)
+        for g in imgs:
+            assert np.array_equal(imgs[g], imgs["0"]), (name, w, h, spp, g)
+        assert np.array_equal(auto, imgs["0"])
+        assert st_auto["rays"] == st_old["rays"] == st["rays"]
+        assert np.allclose(auto, old, rtol=2e-5, atol=1e-6)
+
+
 def test_render_is_deterministic_and_split_invariant(golden):
     """Streams are a pure function of (seed, pixel, sample, bounce): the same call gives the same
     bits, and a frame rendered as two sample ranges sums to the frame rendered in one."""
