@@ -151,6 +151,19 @@ cudaError_t peer_buffer_acquire(int dev, size_t bytes, void **out) {
     for (int i = 0; i < (int)v.size(); ++i)
         if (!v[i].busy && v[i].bytes >= bytes && v[i].bytes <= 2 * bytes + (1u << 20) && (best < 0 || v[i].bytes < v[best].bytes)) best = i;
     if (best < 0) {
+        // a miss means the working set changed (another scene, another resolution): keep at most 1 GiB of idle
+        // buffers per device around, dropping the largest first
+        size_t idle = 0;
+        for (const SharedFrame &f : v) if (!f.busy) idle += f.bytes;
+        while (idle > (1ull << 30)) {
+            int big = -1;
+            for (int i = 0; i < (int)v.size(); ++i)
+                if (!v[i].busy && (big < 0 || v[i].bytes > v[big].bytes)) big = i;
+            if (big < 0) break;
+            idle -= v[big].bytes;
+            cudaFree(v[big].p);
+            v.erase(v.begin() + big);
+        }
         void *p = nullptr;
         cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
         if (e == cudaErrorMemoryAllocation) {   // make room: drop every idle buffer of this device, then retry once
