@@ -831,8 +831,6 @@ int b200rt_scene_create_multi(const B200rtSceneDesc *desc, const B200rtBuildOpts
     for (int i = 0; i < n_devices; ++i) {
         devs[i] = devices ? devices[i] : i;
         if (devs[i] < 0 || devs[i] >= have || devs[i] >= kMaxDevices) return fail(B200RT_EINVAL, "device ordinal out of range");
-        for (int j = 0; j < i; ++j)
-            if (devs[j] == devs[i]) return fail(B200RT_EINVAL, "a device is listed twice");
     }
     if (n_devices == 1) {
         SceneImpl *s = nullptr;
@@ -853,7 +851,7 @@ int b200rt_scene_create_multi(const B200rtSceneDesc *desc, const B200rtBuildOpts
     for (int i = 0; i < n_devices; ++i) {
         DeviceGuard g(devs[i]);
         for (int j = 0; j < n_devices; ++j) {
-            if (i == j) continue;
+            if (devs[i] == devs[j]) continue;   // the same GPU listed again: nothing to map
             int can = 0;
             if (cudaDeviceCanAccessPeer(&can, devs[i], devs[j]) != cudaSuccess) { cudaGetLastError(); can = 0; }
             if (!can) { all_peers = false; continue; }

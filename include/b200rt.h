@@ -173,7 +173,9 @@ void b200rt_scene_destroy(void *scene);
  * copies + accumulate on devices[0] -- and scaled there; the image equals the single-GPU image up to FP32
  * summation order), b200rt_scene_info, b200rt_raycast / b200rt_debug_shade (answered by devices[0]) and
  * b200rt_scene_destroy.  n_devices == 1 is the same as b200rt_scene_create on that device;
- * devices == NULL means devices 0 .. n_devices-1.  No torch, no NCCL, one host thread.  Side effect on the
+ * devices == NULL means devices 0 .. n_devices-1.  A device may be listed more than once: every entry gets its own
+ * copy of the scene, its own stream and its own share of the samples (this is how the test-suite drives the whole
+ * multi-device path -- copies, sample split, fused exchange -- on a one-GPU machine).  No torch, no NCCL, one host thread.  Side effect on the
  * process: cudaDeviceEnablePeerAccess is turned on between the listed devices (and left on); the scene arrays and
  * frames of a multi-device scene are plain cudaMalloc buffers cached per device until b200rt_trim().
  * Replaces: nothing in the reference (it has one CPU); this is how `Camera::render` reaches config 5,

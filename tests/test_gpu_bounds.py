@@ -37,8 +37,15 @@ for name in os.environ["SCENES"].split(","):
             viol = [int(x) for x in dev.bounds_violations()]
         except capi.B200rtError:
             viol = None
-    out[name] = {"viol": viol, "img": hashlib.sha256(img.tobytes()).hexdigest(), "hits": hashlib.sha256(prim.tobytes() + t.tobytes()).hexdigest(),
-                 "rays": st["rays"]}
+    with rt.DeviceSceneHandle(scene, devices=[0, 0]) as dev2:      # the multi-device path (device listed twice), checked too
+        img2, st2 = dev2.render(cam, seed=3)
+        try:
+            viol2 = [int(x) for x in dev2.bounds_violations()]
+        except capi.B200rtError:
+            viol2 = None
+    out[name] = {"viol": viol, "viol_multi": viol2, "img": hashlib.sha256(img.tobytes()).hexdigest(),
+                 "img_multi": hashlib.sha256(img2.tobytes()).hexdigest(),
+                 "hits": hashlib.sha256(prim.tobytes() + t.tobytes()).hexdigest(), "rays": st["rays"], "rays_multi": st2["rays"]}
 # a scene big enough for the GPU LBVH builder (AUTO switches at 65536 primitives)
 rng = np.random.default_rng(5)
 n = 70000
@@ -84,6 +91,9 @@ def test_bounds_checked_build_sees_no_violation_and_the_same_results(dbg_lib):
         assert prod[name]["viol"] is None                       # the production build has no checks compiled in
         assert dbg[name]["img"] == prod[name]["img"], name      # same arithmetic, bit for bit
         assert dbg[name]["rays"] == prod[name]["rays"], name
+        if "viol_multi" in dbg[name]:
+            assert dbg[name]["viol_multi"] == [0, 0, 0, 0], (name, dbg[name]["viol_multi"])
+            assert dbg[name]["img_multi"] == prod[name]["img_multi"] and dbg[name]["rays_multi"] == prod[name]["rays"], name
         if "hits" in dbg[name]:
             assert dbg[name]["hits"] == prod[name]["hits"], name
 

@@ -224,3 +224,36 @@ def test_tonemap_kernel_matches_c_oracle_on_reference_renders(golden, name):
     assert got.shape == want.shape
     assert np.array_equal(got, want), f"{int((got != want).sum())} of {got.size} channels differ"
     assert want.max() > 255 or name == "cornell"     # the no-clamp quirk is exercised
+
+
+def test_more_samples_than_one_launch_holds(golden):
+    """The work pool counts a tile's (pixel, sample) items in 32 bits, so one launch takes at most 2^22 samples per pixel;
+    a longer render goes in several accumulating launches inside the library -- and equals the same split done by hand."""
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    scene = golden.scene("rtow_lights")
+    n = (1 << 22) + 37
+    cam = rt.camera_with(scene.camera, image_w=2, image_h=2, spp=n, max_depth=4)
+    with rt.DeviceSceneHandle(scene) as dev:
+        whole, st = dev.render(cam, seed=3, flags=capi.FLAG_SUM)
+        a, _ = dev.render(cam, seed=3, sample_offset=0, sample_count=1 << 22, flags=capi.FLAG_SUM)
+        b, _ = dev.render(cam, seed=3, sample_offset=1 << 22, sample_count=37, flags=capi.FLAG_SUM)
+        mean, _ = dev.render(cam, seed=3)
+    assert st["paths"] == 4 * n and st["kernel_launches"] == 2
+    assert np.array_equal(whole, a + b)
+    assert np.allclose(mean * n, whole, rtol=1e-6)
+
+
+def test_counters_split_sphere_and_quad_tests_and_trim_keeps_working(golden):
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    for name, all_quads in (("cornell", True), ("rtow_lights", False)):
+        scene = golden.scene(name)
+        cam = rt.camera_with(scene.camera, image_w=64, image_h=48, spp=4)
+        with rt.DeviceSceneHandle(scene) as dev:
+            img, st = dev.render(cam, seed=1, flags=capi.FLAG_COUNTERS)
+            assert st["node_visits"] > 0 and st["prim_tests"] > 0
+            assert st["quad_tests"] == (st["prim_tests"] if all_quads else 0)
+            assert capi.lib().b200rt_trim() == 0            # gives cached device memory back; the handle stays usable
+            again, _ = dev.render(cam, seed=1)
+            assert np.array_equal(img, again)
