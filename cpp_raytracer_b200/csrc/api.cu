@@ -685,7 +685,7 @@ int render_multi(MultiImpl *m, const B200rtCamera *cam, const B200rtRenderOpts *
         const uint64_t lo = count * (uint64_t)d / (uint64_t)n, hi = count * (uint64_t)(d + 1) / (uint64_t)n;
         od.sample_offset = o.sample_offset + lo;
         od.sample_count = hi - lo;
-        od.flags = (o.flags & B200RT_FLAG_COUNTERS) | B200RT_FLAG_SUM | B200RT_FLAG_EXACT_COUNT;
+        od.flags = (o.flags & (B200RT_FLAG_COUNTERS | B200RT_FLAG_THREAD_PIXELS)) | B200RT_FLAG_SUM | B200RT_FLAG_EXACT_COUNT;
         if (int rc = render_on_device(m->dev[d], cam, &od, m->frame[d], m->stream[d], &st[d], false)) return rc;
         CUDA_TRY(cudaEventRecord(m->ev_render[d], m->stream[d]));
     }
