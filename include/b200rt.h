@@ -251,7 +251,9 @@ int b200rt_debug_lane_accounting(void *scene, const B200rtCamera *cam, const B20
 /* Replaces: Camera::render<BVH>(bvh) (camera.h:264-297): for every pixel, the mean (or sum)
  * over the requested samples of ray_color (camera.h:205-258).  out_rgb = image_h x image_w x 3
  * floats, row-major, row 0 at the top, linear HDR (what the reference stores in Image before
- * RGB::as_string tone-maps it). */
+ * RGB::as_string tone-maps it).  The image is a pure function of (scene, camera, seed, sample range): per-pixel sums are
+ * accumulated in 64-bit fixed point (2^-30 units), so they do not depend on how the GPU distributes the samples over its
+ * threads; the sum of one pixel's radiance over one launch (at most 2^22 samples) must stay below 8.6e9. */
 int b200rt_render(void *scene, const B200rtCamera *cam, const B200rtRenderOpts *opts,
                   float *out_rgb, B200rtStats *stats);
 
