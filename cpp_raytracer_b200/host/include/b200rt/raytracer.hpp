@@ -19,8 +19,10 @@
 
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
@@ -31,7 +33,9 @@
 #include <random>
 #include <span>
 #include <string>
+#include <thread>
 #include <type_traits>
+#include <typeinfo>
 #include <unordered_map>
 #include <vector>
 
@@ -257,6 +261,13 @@ inline std::ostream &operator<<(std::ostream &os, const hit_info &info) {       
 struct Hittable {
     // Compound objects return their parts; primitives return {} (hittable.h:112-117).
     virtual std::vector<std::shared_ptr<Hittable>> get_primitive_components() const { return {}; }
+    // Extension used by the flattening step: the same canonical order as get_primitive_components(), as plain
+    // pointers and without copying three million shared_ptrs.  Parts a compound creates on the fly are kept alive in `keep`.
+    virtual void append_primitive_ptrs(std::vector<const Hittable *> &out, std::vector<std::shared_ptr<Hittable>> &keep) const {
+        auto parts = get_primitive_components();
+        if (parts.empty()) { out.push_back(this); return; }
+        for (auto &p : parts) { keep.push_back(p); p->append_primitive_ptrs(out, keep); }
+    }
     virtual void print_to(std::ostream &os) const = 0;
     virtual ~Hittable() = default;
 };
@@ -315,6 +326,9 @@ public:
         }
         return ret;
     }
+    void append_primitive_ptrs(std::vector<const Hittable *> &out, std::vector<std::shared_ptr<Hittable>> &keep) const override {
+        for (const auto &obj : objects) obj->append_primitive_ptrs(out, keep);   // the objects live as long as the scene
+    }
     void print_to(std::ostream &os) const override {
         os << "Scene with " << size() << " objects:\n";
         for (const auto &o : objects) { o->print_to(os); os << '\n'; }
@@ -340,6 +354,9 @@ public:
         faces.add(std::make_shared<Parallelogram>(hi, -sy, -sz, material));
     }
     std::vector<std::shared_ptr<Hittable>> get_primitive_components() const override { return faces.get_primitive_components(); }
+    void append_primitive_ptrs(std::vector<const Hittable *> &out, std::vector<std::shared_ptr<Hittable>> &keep) const override {
+        faces.append_primitive_ptrs(out, keep);
+    }
     void print_to(std::ostream &os) const override { os << "Box {faces: " << faces << "} " << std::flush; }
 };
 
@@ -486,51 +503,190 @@ public:
 // ===== scene flattening (the host half of the drop-in boundary) ==============================
 namespace b200rt_host {
 
+// Plain uninitialised storage for the flat arrays: a std::vector would zero 100+ MB on one thread (and take the page
+// faults there) before the parallel fill overwrites every byte.
+template <typename T>
+class FlatArray {
+    T *p = nullptr;
+    size_t n = 0;
+public:
+    FlatArray() = default;
+    FlatArray(const FlatArray &) = delete;
+    FlatArray &operator=(const FlatArray &) = delete;
+    FlatArray(FlatArray &&o) noexcept : p{o.p}, n{o.n} { o.p = nullptr; o.n = 0; }
+    FlatArray &operator=(FlatArray &&o) noexcept { if (this != &o) { std::free(p); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~FlatArray() { std::free(p); }
+    void resize_uninitialised(size_t count) {
+        std::free(p);
+        p = count ? static_cast<T *>(std::malloc(count * sizeof(T))) : nullptr;
+        n = p ? count : 0;
+        if (count && !p) { std::cout << "Error: out of memory while flattening the scene" << std::endl; std::exit(-1); }
+    }
+    size_t size() const { return n; }
+    bool empty() const { return n == 0; }
+    T *data() { return p; }
+    const T *data() const { return p; }
+    T &operator[](size_t i) { return p[i]; }
+    const T &operator[](size_t i) const { return p[i]; }
+    const T *begin() const { return p; }
+    const T *end() const { return p + n; }
+};
+
 struct FlatScene {
-    std::vector<B200rtMaterial> materials;
-    std::vector<B200rtSphere> spheres;
-    std::vector<B200rtQuad> quads;
+    FlatArray<B200rtMaterial> materials;
+    FlatArray<B200rtSphere> spheres;
+    FlatArray<B200rtQuad> quads;
     B200rtSceneDesc desc() const {
         return B200rtSceneDesc{materials.size(), spheres.size(), quads.size(), materials.data(), spheres.data(), quads.data()};
     }
 };
 
-// Canonical primitive order = get_primitive_components() order (scene.h:85-105); materials are
-// shared by pointer, as the reference's shared_ptr<Material> members are.
+// Runs body(chunk, lo, hi) over [0, n) in `chunks` contiguous pieces on that many threads (inline when one).
+template <typename F>
+inline void for_chunks(size_t n, unsigned chunks, F body) {
+    if (chunks <= 1) { body(0u, (size_t)0, n); return; }
+    std::vector<std::thread> th;
+    for (unsigned c = 0; c < chunks; ++c) th.emplace_back([=, &body] { body(c, n * c / chunks, n * (c + 1) / chunks); });
+    for (auto &t : th) t.join();
+}
+
+// Canonical primitive order = get_primitive_components() order (scene.h:85-105); materials are shared by pointer, as
+// the reference's shared_ptr<Material> members are, and numbered in order of first appearance.
+//   The reference's big scenes hold 2-3 million primitives, each a heap object with its OWN material: walking that
+// pointer graph is latency bound (about 2 s single-threaded with a hash map for the materials -- five times the 8-GPU
+// render of the same scene).  So the walk runs on all host threads, in chunks of top-level objects: pass 1 expands and
+// classifies a chunk and counts; a short serial step turns the counts into offsets and numbers the materials that
+// somebody else also holds (a material with use_count() == 1 never enters the hash map); pass 2 fills the flat arrays,
+// first-touching their pages in parallel.  The result is byte for byte what a serial walk produces
+// (tests/test_host_api_cpu.py compares all ten scenes with dumps of the reference-built objects).
 inline bool flatten(const Scene &world, FlatScene &out, std::string &err) {
     out = FlatScene{};
-    std::unordered_map<const Material *, uint32_t> ids;
-    auto mat_index = [&](const std::shared_ptr<Material> &m) -> uint32_t {
-        auto it = ids.find(m.get());
-        if (it != ids.end()) return it->second;
+    const std::vector<std::shared_ptr<Hittable>> &objects = world;
+    const size_t n_obj = objects.size();
+    unsigned T = n_obj < (1u << 15) ? 1u : std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    if (const char *e = std::getenv("B200RT_FLATTEN_THREADS")) T = (unsigned)std::max(1, std::min(64, std::atoi(e)));
+    // What pass 1 leaves per chunk: the chunk's flat records in order (material and primitive indices still to be
+    // filled in), one tag per primitive, and the materials somebody else also holds (to be numbered globally).
+    enum : uint8_t { kQuad = 1, kShared = 2, kFirst = 4 };
+    struct Chunk {
+        std::vector<B200rtSphere> sph;
+        std::vector<B200rtQuad> quads;
+        std::vector<B200rtMaterial> mats;                    // materials only this primitive holds, in order
+        std::vector<uint8_t> tag;                            // per primitive
+        std::vector<const Material *> shared;                // per primitive with kShared, in order
+        std::vector<uint32_t> shared_u;                      // ... and how many unshared materials preceded it in the chunk
+        std::vector<std::shared_ptr<Hittable>> keep;
+        bool bad = false;
+    };
+    std::vector<Chunk> chunks(T);
+    const bool trace = std::getenv("B200RT_TRACE") != nullptr;
+    auto now = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = trace ? now() : 0;
+    auto material_record = [](const Material *m) {
         B200rtMaterial fm{};
         fm.kind = (uint32_t)m->kind();
-        const RGB c = m->colour();
-        fm.rgb[0] = c.r; fm.rgb[1] = c.g; fm.rgb[2] = c.b;
+        const RGB col = m->colour();
+        fm.rgb[0] = col.r; fm.rgb[1] = col.g; fm.rgb[2] = col.b;
         fm.param = m->param();
-        out.materials.push_back(fm);
-        return ids[m.get()] = (uint32_t)out.materials.size() - 1;
+        return fm;
     };
-    const auto prims = world.get_primitive_components();
-    for (uint32_t i = 0; i < prims.size(); ++i) {
-        const Hittable *h = prims[i].get();
-        if (auto s = dynamic_cast<const Sphere *>(h)) {
-            B200rtSphere f{};
-            f.c[0] = s->center.x; f.c[1] = s->center.y; f.c[2] = s->center.z;
-            f.r = s->radius; f.mat = mat_index(s->material); f.prim = i;
-            out.spheres.push_back(f);
-        } else if (auto q = dynamic_cast<const Parallelogram *>(h)) {
-            B200rtQuad f{};
-            const Point3D &v = q->get_vertex(); const Vec3D &a = q->get_side1(), &b = q->get_side2();
-            f.v[0] = v.x; f.v[1] = v.y; f.v[2] = v.z;
-            f.s1[0] = a.x; f.s1[1] = a.y; f.s1[2] = a.z;
-            f.s2[0] = b.x; f.s2[1] = b.y; f.s2[2] = b.z;
-            f.mat = mat_index(q->get_material()); f.prim = i;
-            out.quads.push_back(f);
-        } else {
-            err = "unsupported Hittable subclass (the device path knows Sphere, Parallelogram, Box and Scene)";
-            return false;
+    // pass 1: expand compounds, classify, read every object ONCE
+    for_chunks(n_obj, T, [&](unsigned c, size_t lo, size_t hi) {
+        Chunk &ch = chunks[c];
+        std::vector<const Hittable *> prims;
+        prims.reserve(hi - lo);
+        for (size_t o = lo; o < hi; ++o) objects[o]->append_primitive_ptrs(prims, ch.keep);
+        ch.tag.resize(prims.size());
+        ch.mats.reserve(prims.size());
+        for (size_t k = 0; k < prims.size(); ++k) {
+            const Hittable *h = prims[k];
+            const std::type_info &ti = typeid(*h);               // exact-type fast path; subclasses go through dynamic_cast
+            const Sphere *s = ti == typeid(Sphere) ? static_cast<const Sphere *>(h) : nullptr;
+            const Parallelogram *q = (!s && ti == typeid(Parallelogram)) ? static_cast<const Parallelogram *>(h) : nullptr;
+            if (!s && !q) { s = dynamic_cast<const Sphere *>(h); if (!s) q = dynamic_cast<const Parallelogram *>(h); }
+            const std::shared_ptr<Material> *mp;
+            uint8_t tag = 0;
+            if (s) {
+                B200rtSphere f{};
+                f.c[0] = s->center.x; f.c[1] = s->center.y; f.c[2] = s->center.z; f.r = s->radius;
+                ch.sph.push_back(f);
+                mp = &s->material;
+            } else if (q) {
+                B200rtQuad f{};
+                const Point3D &v = q->get_vertex(); const Vec3D &a = q->get_side1(), &b = q->get_side2();
+                f.v[0] = v.x; f.v[1] = v.y; f.v[2] = v.z;
+                f.s1[0] = a.x; f.s1[1] = a.y; f.s1[2] = a.z;
+                f.s2[0] = b.x; f.s2[1] = b.y; f.s2[2] = b.z;
+                ch.quads.push_back(f);
+                mp = &q->get_material();
+                tag = kQuad;
+            } else { ch.bad = true; return; }
+            if (mp->use_count() == 1) ch.mats.push_back(material_record(mp->get()));
+            else { tag |= kShared; ch.shared.push_back(mp->get()); ch.shared_u.push_back((uint32_t)ch.mats.size()); }
+            ch.tag[k] = tag;
         }
+    });
+    for (const Chunk &ch : chunks)
+        if (ch.bad) { err = "unsupported Hittable subclass (the device path knows Sphere, Parallelogram, Box and Scene)"; return false; }
+    const double t1 = trace ? now() : 0;
+    // serial step: offsets, and the first appearances of the shared materials in canonical order
+    std::vector<size_t> prim_base(T + 1, 0), sph_base(T + 1, 0), quad_base(T + 1, 0), uniq_base(T + 1, 0), first_base(T + 1, 0);
+    for (unsigned c = 0; c < T; ++c) {
+        prim_base[c + 1] = prim_base[c] + chunks[c].tag.size();
+        sph_base[c + 1] = sph_base[c] + chunks[c].sph.size();
+        quad_base[c + 1] = quad_base[c] + chunks[c].quads.size();
+        uniq_base[c + 1] = uniq_base[c] + chunks[c].mats.size();
+    }
+    if (prim_base[T] > 0x7FFFFFFFull) { err = "too many primitives"; return false; }
+    std::unordered_map<const Material *, uint32_t> shared_id;
+    std::vector<std::vector<uint8_t>> is_first(T);           // per chunk, per shared entry
+    {
+        size_t firsts = 0;
+        for (unsigned c = 0; c < T; ++c) {
+            first_base[c] = firsts;
+            is_first[c].assign(chunks[c].shared.size(), 0);
+            for (size_t j = 0; j < chunks[c].shared.size(); ++j) {
+                const Material *m = chunks[c].shared[j];
+                if (shared_id.count(m)) continue;
+                is_first[c][j] = 1;
+                // id = materials that appeared before this primitive: the unshared ones + the shared ones first seen before it
+                shared_id[m] = (uint32_t)(uniq_base[c] + chunks[c].shared_u[j] + firsts);
+                ++firsts;
+            }
+        }
+        first_base[T] = firsts;
+    }
+    out.spheres.resize_uninitialised(sph_base[T]);
+    out.quads.resize_uninitialised(quad_base[T]);
+    out.materials.resize_uninitialised(uniq_base[T] + first_base[T]);
+    const double t2 = trace ? now() : 0;
+    // pass 2: stream the chunk records into the flat arrays with their final indices (every element written exactly once)
+    for_chunks(T, T, [&](unsigned, size_t c_lo, size_t c_hi) {
+      for (size_t c = c_lo; c < c_hi; ++c) {
+        const Chunk &ch = chunks[c];
+        size_t si = 0, qi = 0, ui = 0, shj = 0, firsts = first_base[c];
+        for (size_t k = 0; k < ch.tag.size(); ++k) {
+            const uint8_t tag = ch.tag[k];
+            uint32_t mat;
+            if (!(tag & kShared)) {
+                mat = (uint32_t)(uniq_base[c] + ui + firsts);
+                out.materials[mat] = ch.mats[ui++];
+            } else {
+                const Material *m = ch.shared[shj];
+                mat = shared_id.find(m)->second;
+                if (is_first[c][shj]) { out.materials[mat] = material_record(m); ++firsts; }
+                ++shj;
+            }
+            const uint32_t prim = (uint32_t)(prim_base[c] + k);
+            if (tag & kQuad) { B200rtQuad f = ch.quads[qi]; f.mat = mat; f.prim = prim; out.quads[quad_base[c] + qi++] = f; }
+            else { B200rtSphere f = ch.sph[si]; f.mat = mat; f.prim = prim; out.spheres[sph_base[c] + si++] = f; }
+        }
+      }
+    });
+    if (trace) {
+        const double t3 = now();
+        chunks.clear();
+        std::fprintf(stderr, "flatten: %u threads, pass 1 %.1f ms, offsets %.1f ms, pass 2 %.1f ms, release %.1f ms\n", T, t1 - t0, t2 - t1, t3 - t2, now() - t3);
     }
     return true;
 }
@@ -693,11 +849,14 @@ public:
 
     static Image to_image(const std::vector<float> &hdr, size_t w, size_t h, double scale = 1.0) {
         Image img = Image::with_dimensions(w, h);
-        for (size_t r = 0; r < h; ++r)
-            for (size_t c = 0; c < w; ++c) {
-                const float *p = &hdr[(r * w + c) * 3];
-                img[r][c] = RGB::from_mag(p[0] * scale, p[1] * scale, p[2] * scale);
-            }
+        const unsigned T = w * h < (1u << 20) ? 1u : std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        b200rt_host::for_chunks(h, T, [&](unsigned, size_t lo, size_t hi) {          // rows are independent
+            for (size_t r = lo; r < hi; ++r)
+                for (size_t c = 0; c < w; ++c) {
+                    const float *p = &hdr[(r * w + c) * 3];
+                    img[r][c] = RGB::from_mag(p[0] * scale, p[1] * scale, p[2] * scale);
+                }
+        });
         return img;
     }
 
@@ -760,6 +919,7 @@ public:
     // camera.h:301-303.  Builds the acceleration structure, uploads, renders on the GPU and
     // returns the linear HDR image, all inside this call.
     Image render(const Scene &world) {
+        const auto t_flat = std::chrono::steady_clock::now();
         b200rt_host::FlatScene flat;
         std::string err;
         if (!b200rt_host::flatten(world, flat, err)) {
@@ -774,10 +934,15 @@ public:
         std::cout << "Rendering " << image_w << " x " << image_h << " image (" << flat.spheres.size() + flat.quads.size()
                   << " primitives, " << samples_per_pixel << " spp) on the GPU..." << std::endl;
         const std::vector<int32_t> devs = devices.empty() ? b200rt_host::default_devices() : devices;
+        const auto t_call = std::chrono::steady_clock::now();
         if (b200rt_render_scene_multi(&desc, &cam, &opts, nullptr, devs.data(), (int32_t)devs.size(), hdr.data(), &last_stats, &last_info) != B200RT_OK) {
             std::cout << "Error: In Camera::render(), " << b200rt_last_error() << std::endl;
             std::exit(-1);
         }
+        if (std::getenv("B200RT_TRACE"))
+            std::fprintf(stderr, "Camera::render: flatten %.1f ms, b200rt_render_scene_multi %.1f ms\n",
+                         std::chrono::duration<double, std::milli>(t_call - t_flat).count(),
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call).count());
         std::cout << "Constructed BVH in " << last_info.build_ms << "ms (created " << last_info.n_nodes << " BVHNodes total); rendered in "
                   << last_stats.kernel_ms << "ms (" << (double)last_stats.paths / last_stats.kernel_ms / 1e3 << " Mpaths/s)\n" << std::endl;
         return to_image(hdr, image_w, image_h);
