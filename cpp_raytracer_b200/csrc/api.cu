@@ -353,14 +353,17 @@ int render_on_device(SceneImpl *s, const B200rtCamera *cam, const B200rtRenderOp
         CUDA_TRY(run_wavefront(s->stack, P, W, (o.flags & B200RT_FLAG_COUNTERS) != 0, st, s->sm_count, &launches));
         CUDA_TRY(cudaEventRecord(s->ev_pool, st));
     } else {
-        // the tile work pool counts (pixel, sample) items in 32 bits: more than 2^24 samples per pixel go in several launches
+        // order of the node and the leaf step inside a traversal iteration (traverse.cuh): leaf first when quads dominate
+        bool leaf_first = s->info.n_quads > s->info.n_spheres;
+        if (const char *lf = std::getenv("B200RT_LEAF_FIRST")) leaf_first = lf[0] == '1';   // experiments
+        // the tile work pool counts (pixel, sample) items in 32 bits: more than 2^22 samples per pixel go in several launches
         launches = 0;
         for (uint64_t done = 0; done < count; done += kMaxSamplesPerLaunch) {
             RenderParams Q = P;
             Q.sample_begin = (uint32_t)(o.sample_offset + done);
             Q.sample_count = (uint32_t)std::min<uint64_t>(kMaxSamplesPerLaunch, count - done);
             if (done) Q.flags |= kRenderAccumulate;
-            CUDA_TRY(launch_path_megakernel(s->stack, Q, (o.flags & B200RT_FLAG_COUNTERS) != 0, s->info.tree_depth <= 3, st));
+            CUDA_TRY(launch_path_megakernel(s->stack, Q, (o.flags & B200RT_FLAG_COUNTERS) != 0, leaf_first, st));
             ++launches;
         }
     }
@@ -1048,7 +1051,7 @@ int b200rt_debug_lane_accounting(void *scene, const B200rtCamera *cam, const B20
     P.scene = s->d; P.seed = o.seed; P.sample_begin = (uint32_t)o.sample_offset; P.sample_count = (uint32_t)count;
     P.out = d_frame; P.flags = o.flags & B200RT_FLAG_THREAD_PIXELS; P.scale = 1.0f; P.counters = s->d_counters;
     P.group_shift = (cam->background[0] == 0.0 && cam->background[1] == 0.0 && cam->background[2] == 0.0) ? 3u : 0u;
-    if (e == cudaSuccess) e = launch_path_lanes(s->stack, P, d_acc, 0);
+    if (e == cudaSuccess) e = launch_path_lanes(s->stack, P, d_acc, s->info.n_quads > s->info.n_spheres, 0);
     if (e == cudaSuccess) e = cudaMemcpy(counters_out, d_acc, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
     cudaStreamSynchronize(0);
     dev_free(d_frame); dev_free(d_acc);

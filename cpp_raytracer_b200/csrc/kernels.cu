@@ -337,7 +337,7 @@ __device__ __forceinline__ void write_counters(const RenderParams &P, uint32_t l
 
 // path_megakernel_pool (variant 0, default): every lane runs traverse-then-shade in a loop and takes the tile's next
 // (pixel, sample) item as soon as its path ends.
-template <int STACK, bool COUNT, bool SHALLOW = false, int MINB = kPathMinBlocks>
+template <int STACK, bool COUNT, bool LEAF_FIRST = false, int MINB = kPathMinBlocks>
 __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel_pool(const __grid_constant__ RenderParams P) {
     __shared__ TilePool tp;
     const CameraParams &C = P.cam;
@@ -350,7 +350,7 @@ __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel_pool(const _
     Hit best{0.0, kNoHit};
     while (pool_shade_and_advance(P, tm, tp, total_items, best, L, ray)) {
         // world.hit_by(ray, Interval::with_min(0.00001))  (camera.h:217)
-        best = closest_hit<STACK, COUNT, SHALLOW>(P.scene, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, 0.00001,
+        best = closest_hit<STACK, COUNT, LEAF_FIRST>(P.scene, ray.ox, ray.oy, ray.oz, ray.dx, ray.dy, ray.dz, 0.00001,
                                                   __longlong_as_double(0x7ff0000000000000LL), &ctr);
     }
     pool_write_tile(P, tm, tp);
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel_pool(const _
 // path_megakernel (thread-owns-pixel form, kept for A/B: B200RT_FLAG_THREAD_PIXELS): every lane runs traverse-then-shade
 // in a loop over ITS pixel's samples and starts the next sample as soon as a path ends.  64 registers (16 blocks = 32 warps per SM) measured
 // fastest on B200: 8/12/16/20/24 blocks per SM gave 2707/3171/3263/2630/2307 Mpaths/s on C2.
-template <int STACK, bool COUNT, bool SHALLOW = false, int MINB = kPathMinBlocks>
+template <int STACK, bool COUNT, bool LEAF_FIRST = false, int MINB = kPathMinBlocks>
 __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel(const __grid_constant__ RenderParams P) {
     const CameraParams &C = P.cam;
     const PixelMap m = map_pixel(C);
@@ -371,7 +371,7 @@ __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel(const __grid
     if (m.valid && C.max_depth > 0 && P.sample_count > 0) {
         while (shade_and_advance(P, m, best, L)) {
             // world.hit_by(ray, Interval::with_min(0.00001))  (camera.h:217)
-            best = closest_hit<STACK, COUNT, SHALLOW>(P.scene, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001,
+            best = closest_hit<STACK, COUNT, LEAF_FIRST>(P.scene, L.ray.ox, L.ray.oy, L.ray.oz, L.ray.dx, L.ray.dy, L.ray.dz, 0.00001,
                                              __longlong_as_double(0x7ff0000000000000LL), &ctr);
         }
     }
@@ -380,8 +380,8 @@ __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel(const __grid
 
 // ------------------------------------------------------------------------------------------
 // path_lanes_kernel: MEASUREMENT ONLY (b200rt_debug_lane_accounting).  The default kernel's schedule -- per
-// round every lane shades / regenerates, then the warp runs one traversal step per lane per iteration until
-// its slowest lane is done -- replayed warp-synchronously so that each warp can count, per executed step,
+// round every lane shades / regenerates, then the warp iterates "node step for the lanes at a node, leaf step for the
+// lanes at a leaf" (or the reverse order, as the launcher picks) until its slowest lane is done -- replayed warp-synchronously so that each warp can count, per executed step,
 // how many of its 32 lanes took part and what the others were doing:
 //   acc[0] shade executions           acc[1] lanes taking part
 //   acc[2] node-step executions       acc[3] lanes at a node     acc[4] idle: at a leaf   acc[5] idle: traversal done,
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(kPathBlock, MINB) path_megakernel(const __grid
 //   acc[14] warps   acc[15] lane-rounds (shade calls that started a ray)
 // Same Philox keys and the same arithmetic as path_megakernel, so it also writes the same image.
 template <int STACK, bool POOL>
-__global__ void __launch_bounds__(kPathBlock) path_lanes_kernel(const __grid_constant__ RenderParams P, unsigned long long *__restrict__ acc) {
+__global__ void __launch_bounds__(kPathBlock) path_lanes_kernel(const __grid_constant__ RenderParams P, unsigned long long *__restrict__ acc, bool leaf_first) {
     __shared__ TilePool tp;
     const CameraParams &C = P.cam;
     const PixelMap m = map_pixel(C);
@@ -423,23 +423,30 @@ __global__ void __launch_bounds__(kPathBlock) path_lanes_kernel(const __grid_con
             if (go) a[15]++;
             else { finished = true; T.cur = kTravDone; }
         }
-        while (true) {
-            const bool node = !finished && trav_at_node(T), leaf = !finished && trav_at_leaf(T);
-            const unsigned mn = __ballot_sync(full, node), ml = __ballot_sync(full, leaf), mf = __ballot_sync(full, finished);
-            if (!(mn | ml)) break;
-            const unsigned md = ~(mn | ml | mf);
-            if (mn) { a[2]++; a[3] += __popc(mn); a[4] += __popc(ml); a[5] += __popc(md); a[6] += __popc(mf); }
-            if (ml) {
-                a[7]++; a[8] += __popc(ml); a[9] += __popc(mn); a[10] += __popc(md); a[11] += __popc(mf);
-                const uint32_t cnt = leaf ? ((T.cur >> 26) & 0xFu) : 0u;
-                for (uint32_t i = 0; i < 8; ++i) {
-                    const unsigned mi = __ballot_sync(full, cnt > i);
-                    if (!mi) break;
-                    a[12]++; a[13] += __popc(mi);
+        while (true) {   // one iteration of closest_hit's loop: both kinds of step, in the product's order
+            if (!__ballot_sync(full, !finished && !trav_done(T))) break;
+#pragma unroll
+            for (int phase = 0; phase < 2; ++phase) {
+                const bool node_phase = (phase == 0) != leaf_first;
+                const bool node = !finished && trav_at_node(T), leaf = !finished && trav_at_leaf(T);
+                const unsigned mn = __ballot_sync(full, node), ml = __ballot_sync(full, leaf), mf = __ballot_sync(full, finished);
+                const unsigned md = ~(mn | ml | mf);
+                if (node_phase) {
+                    if (mn) { a[2]++; a[3] += __popc(mn); a[4] += __popc(ml); a[5] += __popc(md); a[6] += __popc(mf); }
+                    if (node) trav_node_step(P.scene, T, stack);
+                } else {
+                    if (ml) {
+                        a[7]++; a[8] += __popc(ml); a[9] += __popc(mn); a[10] += __popc(md); a[11] += __popc(mf);
+                        const uint32_t cnt = leaf ? ((T.cur >> 26) & 0xFu) : 0u;
+                        for (uint32_t i = 0; i < 8; ++i) {
+                            const unsigned mi = __ballot_sync(full, cnt > i);
+                            if (!mi) break;
+                            a[12]++; a[13] += __popc(mi);
+                        }
+                    }
+                    if (leaf) trav_leaf_step(P.scene, T, stack);
                 }
             }
-            if (node) trav_node_step(P.scene, T, stack);
-            else if (leaf) trav_leaf_step(P.scene, T, stack);
         }
     }
     TraversalCounters ctr;
@@ -609,38 +616,35 @@ cudaError_t launch_debug_shade(int stack, const DeviceScene &S, const double *ra
 }
 
 template <int STACK>
-static cudaError_t launch_path_t(const RenderParams &P, bool count, bool shallow, cudaStream_t st) {
+static cudaError_t launch_path_t(const RenderParams &P, bool count, bool leaf_first, cudaStream_t st) {
     const uint32_t tiles = ((P.cam.w + (uint32_t)kPathTileW - 1u) / (uint32_t)kPathTileW) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
     if (tiles == 0) return cudaSuccess;
     if (!(P.flags & kRenderThreadPixels)) {
-        if (STACK == 32 && shallow) {   // trees of depth <= 3 (a handful of nodes): while-while loop structure
-            if (count) path_megakernel_pool<32, true, true><<<tiles, kPathBlock, 0, st>>>(P);
-            else path_megakernel_pool<32, false, true><<<tiles, kPathBlock, 0, st>>>(P);
+        if (leaf_first) {
+            if (count) path_megakernel_pool<STACK, true, true><<<tiles, kPathBlock, 0, st>>>(P);
+            else path_megakernel_pool<STACK, false, true><<<tiles, kPathBlock, 0, st>>>(P);
         } else if (count) path_megakernel_pool<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
         else path_megakernel_pool<STACK, false><<<tiles, kPathBlock, 0, st>>>(P);
         return cudaGetLastError();
     }
-    if (STACK == 32 && shallow) {   // trees of depth <= 3 (a handful of nodes): while-while loop structure
-        if (count) path_megakernel<32, true, true><<<tiles, kPathBlock, 0, st>>>(P);
-        else path_megakernel<32, false, true><<<tiles, kPathBlock, 0, st>>>(P);
-    } else if (count) path_megakernel<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);
+    if (count) path_megakernel<STACK, true><<<tiles, kPathBlock, 0, st>>>(P);      // round-1 work distribution: node-then-leaf only
     else path_megakernel<STACK, false><<<tiles, kPathBlock, 0, st>>>(P);
     return cudaGetLastError();
 }
 
-cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool shallow, cudaStream_t st) {
-    if (stack <= 32) return launch_path_t<32>(P, count, shallow, st);
-    if (stack <= 64) return launch_path_t<64>(P, count, false, st);
-    return launch_path_t<128>(P, count, false, st);
+cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool leaf_first, cudaStream_t st) {
+    if (stack <= 32) return launch_path_t<32>(P, count, leaf_first, st);
+    if (stack <= 64) return launch_path_t<64>(P, count, leaf_first, st);
+    return launch_path_t<128>(P, count, leaf_first, st);
 }
 
-cudaError_t launch_path_lanes(int stack, const RenderParams &P, unsigned long long *acc, cudaStream_t st) {
+cudaError_t launch_path_lanes(int stack, const RenderParams &P, unsigned long long *acc, bool leaf_first, cudaStream_t st) {
     const uint32_t tiles = ((P.cam.w + (uint32_t)kPathTileW - 1u) / (uint32_t)kPathTileW) * ((P.cam.h + (uint32_t)kPathTileH - 1u) / (uint32_t)kPathTileH);
     if (tiles == 0) return cudaSuccess;
     const bool pool = !(P.flags & kRenderThreadPixels);
-    if (stack <= 32) { if (pool) path_lanes_kernel<32, true><<<tiles, kPathBlock, 0, st>>>(P, acc); else path_lanes_kernel<32, false><<<tiles, kPathBlock, 0, st>>>(P, acc); }
-    else if (stack <= 64) { if (pool) path_lanes_kernel<64, true><<<tiles, kPathBlock, 0, st>>>(P, acc); else path_lanes_kernel<64, false><<<tiles, kPathBlock, 0, st>>>(P, acc); }
-    else { if (pool) path_lanes_kernel<128, true><<<tiles, kPathBlock, 0, st>>>(P, acc); else path_lanes_kernel<128, false><<<tiles, kPathBlock, 0, st>>>(P, acc); }
+    if (stack <= 32) { if (pool) path_lanes_kernel<32, true><<<tiles, kPathBlock, 0, st>>>(P, acc, leaf_first); else path_lanes_kernel<32, false><<<tiles, kPathBlock, 0, st>>>(P, acc, leaf_first); }
+    else if (stack <= 64) { if (pool) path_lanes_kernel<64, true><<<tiles, kPathBlock, 0, st>>>(P, acc, leaf_first); else path_lanes_kernel<64, false><<<tiles, kPathBlock, 0, st>>>(P, acc, leaf_first); }
+    else { if (pool) path_lanes_kernel<128, true><<<tiles, kPathBlock, 0, st>>>(P, acc, leaf_first); else path_lanes_kernel<128, false><<<tiles, kPathBlock, 0, st>>>(P, acc, leaf_first); }
     return cudaGetLastError();
 }
 

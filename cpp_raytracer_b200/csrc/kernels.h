@@ -75,10 +75,10 @@ cudaError_t run_wavefront(int stack, const RenderParams &P, const WavefrontPool 
 // launchers pick the smallest instantiation that fits (32 / 64 / 128).
 cudaError_t launch_raycast(int stack, const DeviceScene &S, const double *rays, long long n, double tmin, double tmax,
                            int32_t *prim, double *t, cudaStream_t st);
-// shallow: the tree has depth <= 3 -> while-while traversal loop (see closest_hit)
-cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool shallow, cudaStream_t st);
+// leaf_first: order of the two steps inside one iteration of the traversal loop (see closest_hit)
+cudaError_t launch_path_megakernel(int stack, const RenderParams &P, bool count, bool leaf_first, cudaStream_t st);
 // measurement only: 16 lane-accounting counters (see path_lanes_kernel)
-cudaError_t launch_path_lanes(int stack, const RenderParams &P, unsigned long long *acc, cudaStream_t st);
+cudaError_t launch_path_lanes(int stack, const RenderParams &P, unsigned long long *acc, bool leaf_first, cudaStream_t st);
 cudaError_t launch_finalize(float *frame, long long n_pixels, float scale, int32_t *ldr, int clamp, cudaStream_t st);
 cudaError_t launch_tonemap(const float *hdr, long long n_pixels, int32_t *out, int clamp, cudaStream_t st);
 cudaError_t launch_debug_camera(const CameraParams &C, const uint32_t *pixels, const uint32_t *rnd, long long n, double *rays_out,

@@ -348,41 +348,35 @@ __device__ __forceinline__ uint32_t trav_leaf_step(const DeviceScene &S, Trav &T
     return cnt;
 }
 
-// SHALLOW selects the loop structure.  Default: one step (node or leaf) per iteration, lanes re-converge every
-// iteration.  SHALLOW ("while-while"): consecutive node steps, then consecutive leaves; measured +9 % on the
-// Cornell box (tree of depth 3: 3.4 node steps and 1.8 FP64 quad tests per ray, so lanes at a leaf rarely wait
-// long for the others to leave the node loop) and -1 ... -18 % on the deeper trees of every other scene.
-template <int STACK, bool COUNT, bool SHALLOW = false>
+// The traversal loop.  Every iteration offers a lane BOTH kinds of step, one after the other: with NODE-then-LEAF order
+// a lane whose node step lands on a leaf tests that leaf in the same iteration, together with the lanes that were
+// already at a leaf -- so the expensive FP64 leaf code, the most lane-starved code of the kernel, runs with more
+// lanes per execution and the ray needs fewer iterations (a ray's N N L N L takes three iterations instead of
+// five).  LEAF_FIRST is the mirror image (a lane that pops a node after its leaf visits it at once): it packs the NODE
+// step instead.  Measured against round 1's "one step per iteration" loop (B200, 256-512 spp, same-box A/B):
+// node-then-leaf C1 +6.5 %, C2 +5.7 %, C3 +4.6 %, C4 -1.3 %, C4b -1 %, C5 +4.4 %; leaf-then-node C1 +6.5 %, C2 +3.7 %,
+// C3 +4.7 %, C4 0 %, C4b +2.5 %, C5 +3.2 %.  The launcher uses leaf-first when quads outnumber spheres.  Two steps of a
+// kind per iteration (L N L, N L N) lose again (-1 ... +1 %), and so did round 1's while-while form, which these loops
+// replace even on the depth-3 Cornell tree (+4.6 % over it).
+template <int STACK, bool COUNT, bool LEAF_FIRST = false>
 __device__ __forceinline__ Hit closest_hit(const DeviceScene &S, double ox, double oy, double oz,
                                            double dx, double dy, double dz, double tmin, double tmax,
                                            TraversalCounters *ctr) {
     Trav T;
     uint2 stack[STACK];
     trav_init(T, ox, oy, oz, dx, dy, dz, tmin, tmax);
-    if (SHALLOW) {
-        while (!trav_done(T)) {
-            while (trav_at_node(T)) {
-                if (COUNT) ctr->nodes++;
-                trav_node_step(S, T, stack);
-            }
-            while (trav_at_leaf(T)) {
-                const bool is_quad = T.cur & kQuadFlagD;
-                const uint32_t c = trav_leaf_step(S, T, stack);
-                if (COUNT) { ctr->prims += c; if (is_quad) ctr->quads += c; }
-            }
-        }
-        return T.best;
+#define B200RT_NODE_ if (trav_at_node(T)) { if (COUNT) ctr->nodes++; trav_node_step(S, T, stack); }
+#define B200RT_LEAF_ if (trav_at_leaf(T)) {                                                     \
+        const bool is_quad = T.cur & kQuadFlagD;                                                \
+        const uint32_t c = trav_leaf_step(S, T, stack);                                         \
+        if (COUNT) { ctr->prims += c; if (is_quad) ctr->quads += c; }                           \
     }
     while (!trav_done(T)) {
-        if (trav_at_node(T)) {
-            if (COUNT) ctr->nodes++;
-            trav_node_step(S, T, stack);
-        } else {
-            const bool is_quad = T.cur & kQuadFlagD;
-            const uint32_t c = trav_leaf_step(S, T, stack);
-            if (COUNT) { ctr->prims += c; if (is_quad) ctr->quads += c; }
-        }
+        if (LEAF_FIRST) { B200RT_LEAF_ B200RT_NODE_ }
+        else { B200RT_NODE_ B200RT_LEAF_ }
     }
+#undef B200RT_NODE_
+#undef B200RT_LEAF_
     return T.best;
 }
 

@@ -138,10 +138,11 @@ __global__ void __launch_bounds__(kPathBlock, kPathMinBlocks) wf_trace(const __g
             }
         }
         if (have) {
-            if (trav_at_node(T)) {
+            if (trav_at_node(T)) {          // node step, then -- same iteration -- the leaf it may have landed on (see closest_hit)
                 if (COUNT) ctr.nodes++;
                 trav_node_step(P.scene, T, stack);
-            } else {
+            }
+            if (trav_at_leaf(T)) {
                 const bool is_quad = T.cur & kQuadFlagD;
                 const uint32_t c = trav_leaf_step(P.scene, T, stack);
                 if (COUNT) { ctr.prims += c; if (is_quad) ctr.quads += c; }
