@@ -236,6 +236,43 @@ __device__ __forceinline__ void pool_contribute(TilePool &tp, uint32_t lp, float
     if (b != 0.0f) atomicAdd(reinterpret_cast<unsigned long long *>(&tp.acc[lp * 3 + 2]), (unsigned long long)__float2ll_rn(b * kFixScale));
 }
 
+// Takes the tile's next (pixel, sample) item into L (false: none left).  Item order: group_shift = 0: sample-major
+// (consecutive items = neighbouring pixels of one sample).  group_shift = g: consecutive items = 2^g samples of the SAME
+// pixel, so the primary rays a warp starts together are near-identical and traverse in lockstep: C2 +3 %, C4 +5 %,
+// C4b +15 %, C5 +5 % -- when the background is black.  With a bright background every escaping path adds to its pixel's
+// accumulator and lanes on the same pixel serialise on it (C1 -3 %; warp-aggregating the sums first costs more than it
+// saves), so the host picks g = 3 for a black background and 0 otherwise (profiles/r2_tile_shape.md).  The image is the same
+// bit for bit under every order.
+__device__ __forceinline__ bool pool_fetch(const RenderParams &P, const TileMap &tm, TilePool &tp, uint32_t total_items, PoolLane &L,
+                                           uint32_t &px, uint32_t &py) {
+    if (total_items == 0u) return false;
+    const uint32_t gs = P.group_shift;
+    if (gs == 0u) {
+        const uint32_t item = atomicAdd(&tp.next, 1u);
+        if (item >= total_items) return false;
+        if (tm.n_valid == (uint32_t)kPathBlock) { L.s = item / (uint32_t)kPathBlock; L.lp = item % (uint32_t)kPathBlock; }
+        else { L.s = item / tm.n_valid; L.lp = item - L.s * tm.n_valid; }
+    } else {
+        const uint32_t per_block = tm.n_valid << gs;                             // items per block of 2^g samples
+        const uint32_t limit = per_block * ((P.sample_count + (1u << gs) - 1u) >> gs);
+        while (true) {
+            const uint32_t item = atomicAdd(&tp.next, 1u);
+            if (item >= limit) return false;
+            const uint32_t s_hi = item / per_block, rem = item - s_hi * per_block;
+            L.lp = rem >> gs;
+            L.s = (s_hi << gs) + (rem & ((1u << gs) - 1u));
+            if (L.s < P.sample_count) break;                                      // ragged last block of samples
+        }
+    }
+    const uint32_t lx = tm.vw == (uint32_t)kPathTileW ? L.lp % (uint32_t)kPathTileW : L.lp % tm.vw;
+    const uint32_t ly = tm.vw == (uint32_t)kPathTileW ? L.lp / (uint32_t)kPathTileW : L.lp / tm.vw;
+    px = tm.x0 + lx;
+    py = tm.y0 + ly;
+    L.pixel = py * P.cam.w + px;
+    L.bounce = 0;
+    return true;
+}
+
 // shade_and_advance with the tile pool: same path semantics, same Philox keys (pixel, sample, bounce).
 __device__ __forceinline__ bool pool_shade_and_advance(const RenderParams &P, const TileMap &tm, TilePool &tp, uint32_t total_items,
                                                        const Hit &best, PoolLane &L, Ray &ray) {
@@ -258,39 +295,10 @@ __device__ __forceinline__ bool pool_shade_and_advance(const RenderParams &P, co
         if (!cont) L.has_path = false;
     }
     if (!L.has_path) {
-        // Item order.  group_shift = 0: sample-major (consecutive items = neighbouring pixels of one sample).
-        // group_shift = g: consecutive items = 2^g samples of the SAME pixel, so the primary rays a warp starts together
-        // are near-identical and traverse in lockstep: C2 +3 %, C4 +5 %, C4b +15 %, C5 +5 % -- when the background is
-        // black.  With a bright background every escaping path adds to its pixel's accumulator and lanes on the same
-        // pixel serialise on it (C1 -3 %; warp-aggregating the sums first costs more than it saves), so the host
-        // picks g = 3 for a black background and 0 otherwise (profiles/r2_tile_shape.md).  The image is the same bit for
-        // bit under every order.
-        if (total_items == 0u) return false;
-        const uint32_t gs = P.group_shift;
-        if (gs == 0u) {
-            const uint32_t item = atomicAdd(&tp.next, 1u);
-            if (item >= total_items) return false;
-            if (tm.n_valid == (uint32_t)kPathBlock) { L.s = item / (uint32_t)kPathBlock; L.lp = item % (uint32_t)kPathBlock; }
-            else { L.s = item / tm.n_valid; L.lp = item - L.s * tm.n_valid; }
-        } else {
-            const uint32_t per_block = tm.n_valid << gs;                             // items per block of 2^g samples
-            const uint32_t limit = per_block * ((P.sample_count + (1u << gs) - 1u) >> gs);
-            while (true) {
-                const uint32_t item = atomicAdd(&tp.next, 1u);
-                if (item >= limit) return false;
-                const uint32_t s_hi = item / per_block, rem = item - s_hi * per_block;
-                L.lp = rem >> gs;
-                L.s = (s_hi << gs) + (rem & ((1u << gs) - 1u));
-                if (L.s < P.sample_count) break;                                      // ragged last block of samples
-            }
-        }
-        const uint32_t lx = tm.vw == (uint32_t)kPathTileW ? L.lp % (uint32_t)kPathTileW : L.lp % tm.vw;
-        const uint32_t ly = tm.vw == (uint32_t)kPathTileW ? L.lp / (uint32_t)kPathTileW : L.lp / tm.vw;
-        const uint32_t px = tm.x0 + lx, py = tm.y0 + ly;
-        L.pixel = py * C.w + px;
+        uint32_t px, py;
+        if (!pool_fetch(P, tm, tp, total_items, L, px, py)) return false;
         const Philox4 rnd = philox4x32_10(L.pixel, P.sample_begin + L.s, 0u, 0u, k0, k1);
         camera_ray(C, px, py, rnd, ray, L.p);
-        L.bounce = 0;
         L.has_path = true;
     }
     return true;
