@@ -136,6 +136,36 @@ def test_compute_fails_loudly_without_gpu(golden):
     with pytest.raises(rt.B200rtError) as e:
         rt.tonemap(np.zeros((4, 3), np.float32))
     assert e.value.code == capi.ENODEVICE
+    # the entries added in ABI v2 behave the same: the multi-device forms, the one-call render, the test hooks
+    scene = golden.scene("quads")
+    cam = rt.camera_with(scene.camera, image_w=8, image_h=8, spp=1)
+    with pytest.raises(rt.B200rtError) as e:
+        rt.DeviceSceneHandle(scene, devices=[0, 1])
+    assert e.value.code == capi.ENODEVICE
+    for devices in (None, [0], [0, 0]):
+        with pytest.raises(rt.B200rtError) as e:
+            rt.render_scene(scene, cam, devices=devices)
+        assert e.value.code == capi.ENODEVICE
+    with pytest.raises(rt.B200rtError) as e:
+        capi.debug_philox(np.zeros((1, 6), np.uint32))
+    assert e.value.code == capi.ENODEVICE
+    with pytest.raises(rt.B200rtError) as e:
+        capi.debug_samplers(np.zeros((1, 2), np.uint32))
+    assert e.value.code == capi.ENODEVICE
+    assert capi.lib().b200rt_trim() == 0          # nothing cached, nothing to do: not an error
+
+
+def test_scene_description_is_validated_before_any_device_is_needed(golden):
+    """Malformed descriptions are EINVAL whether or not a GPU is present (structure checks come first)."""
+    import ctypes
+    import cpp_raytracer_b200 as rt
+    from cpp_raytracer_b200 import capi
+    h = ctypes.c_void_p()
+    assert capi.lib().b200rt_scene_create(None, None, ctypes.byref(h)) == capi.EINVAL
+    desc = capi.SceneDesc(0, 3, 0, None, None, None)        # a count without an array
+    assert capi.lib().b200rt_scene_create(ctypes.byref(desc), None, ctypes.byref(h)) == capi.EINVAL
+    assert capi.lib().b200rt_scene_create_multi(ctypes.byref(desc), None, None, 2, ctypes.byref(h)) == capi.EINVAL
+    assert b"count without an array" in capi.lib().b200rt_last_error()
 
 
 def test_sample_ranges_tile_exactly():
