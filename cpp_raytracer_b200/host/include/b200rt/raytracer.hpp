@@ -744,12 +744,18 @@ public:
     BVH(const T &world, size_t num_buckets = 32, size_t max_primitives_in_node = 12, std::vector<int32_t> devices = {})
         : primitives{world.get_primitive_components()} {
         if (devices.empty()) devices = b200rt_host::default_devices();
-        Scene flat_world;
-        if (primitives.empty()) primitives.push_back(std::shared_ptr<Hittable>(std::shared_ptr<Hittable>{}, const_cast<T *>(&world)));
-        for (const auto &p : primitives) flat_world.add(p);
         b200rt_host::FlatScene flat;
         std::string err;
-        if (!b200rt_host::flatten(flat_world, flat, err)) {
+        bool ok;
+        if constexpr (std::is_same_v<T, Scene>) {
+            ok = b200rt_host::flatten(world, flat, err);        // same canonical order, without a second copy of every shared_ptr
+        } else {
+            Scene flat_world;
+            if (primitives.empty()) primitives.push_back(std::shared_ptr<Hittable>(std::shared_ptr<Hittable>{}, const_cast<T *>(&world)));
+            for (const auto &p : primitives) flat_world.add(p);
+            ok = b200rt_host::flatten(flat_world, flat, err);
+        }
+        if (!ok) {
             std::cout << "Error: In BVH::BVH(), " << err << std::endl;
             std::exit(-1);
         }
